@@ -1,0 +1,111 @@
+"""ctypes binding of include/hrl_b200.h (the C ABI of the CUDA library).
+
+The library is built in-tree by `__graft_entry__.build()` / `handyrl_b200/csrc/build.py`
+into handyrl_b200/libhrl_b200.so.  There is NO fallback: if the library is missing or a
+symbol is absent, importing `lib()` raises.
+"""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libhrl_b200.so')
+
+HRL_ABI_VERSION = 1
+ALGO_ID = {'MC': 0, 'TD': 1, 'UPGO': 2, 'VTRACE': 3}
+LOSS_KEYS = ('p', 'v', 'r', 'ent', 'total', 'dcnt')
+NUM_LOSS = 6
+
+_f32p = C.POINTER(C.c_float)
+_i64p = C.POINTER(C.c_int64)
+
+
+class HrlLossArgs(C.Structure):
+    _fields_ = [
+        ('B', C.c_int32), ('T', C.c_int32), ('P', C.c_int32), ('Pa', C.c_int32), ('A', C.c_int32),
+        ('burn_in', C.c_int32), ('value_target', C.c_int32), ('policy_target', C.c_int32),
+        ('two_player_zero_sum', C.c_int32),
+        ('lambda_', C.c_float), ('gamma', C.c_float),
+        ('entropy_regularization', C.c_float), ('entropy_regularization_decay', C.c_float),
+        ('policy_raw', C.c_void_p), ('value_raw', C.c_void_p), ('return_raw', C.c_void_p),
+        ('action_mask', C.c_void_p), ('action', C.c_void_p), ('selected_prob', C.c_void_p),
+        ('reward', C.c_void_p), ('ret', C.c_void_p), ('turn_mask', C.c_void_p),
+        ('observation_mask', C.c_void_p), ('episode_mask', C.c_void_p), ('progress', C.c_void_p),
+        ('outcome', C.c_void_p),
+        ('dpolicy_raw', C.c_void_p), ('dvalue_raw', C.c_void_p), ('dreturn_raw', C.c_void_p),
+        ('losses', C.c_void_p),
+        ('tap_target_value', C.c_void_p), ('tap_target_return', C.c_void_p), ('tap_advantage', C.c_void_p),
+        ('tap_logp', C.c_void_p), ('tap_rho', C.c_void_p), ('tap_entropy', C.c_void_p),
+        ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+    ]
+
+
+class HrlWindow(C.Structure):
+    _fields_ = [('first_step', C.c_int64), ('start', C.c_int32), ('end', C.c_int32),
+                ('train_start', C.c_int32), ('total', C.c_int32), ('outcome_row', C.c_int32),
+                ('reserved', C.c_int32)]
+
+
+class HrlGatherArgs(C.Structure):
+    _fields_ = [
+        ('B', C.c_int32), ('T', C.c_int32), ('P', C.c_int32), ('Pa', C.c_int32), ('A', C.c_int32),
+        ('burn_in', C.c_int32), ('obs_elems', C.c_int32), ('turn_alternating', C.c_int32),
+        ('windows', C.c_void_p),
+        ('st_obs', C.c_void_p), ('st_prob', C.c_void_p), ('st_action', C.c_void_p), ('st_amask', C.c_void_p),
+        ('st_value', C.c_void_p), ('st_reward', C.c_void_p), ('st_return', C.c_void_p),
+        ('st_flags', C.c_void_p), ('st_turn', C.c_void_p), ('st_outcome', C.c_void_p),
+        ('observation', C.c_void_p), ('selected_prob', C.c_void_p), ('value', C.c_void_p),
+        ('action', C.c_void_p), ('outcome', C.c_void_p), ('reward', C.c_void_p), ('ret', C.c_void_p),
+        ('episode_mask', C.c_void_p), ('turn_mask', C.c_void_p), ('observation_mask', C.c_void_p),
+        ('action_mask', C.c_void_p), ('progress', C.c_void_p),
+    ]
+
+
+# every symbol include/hrl_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    'hrl_loss_workspace_bytes': (C.c_size_t, [C.c_int32] * 5),
+    'hrl_loss_fwd_bwd': (C.c_int, [C.POINTER(HrlLossArgs), C.c_void_p]),
+    'hrl_compute_target': (C.c_int, [C.c_int32] * 6 + [C.c_void_p] * 3 + [C.c_float, C.c_float] +
+                           [C.c_void_p] * 5 + [C.c_void_p]),
+    'hrl_sumsq_num_partials': (C.c_int32, []),
+    'hrl_grad_sumsq': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'hrl_clip_adam_step': (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 3 +
+                           [C.c_float] * 5 + [C.c_void_p, C.c_void_p]),
+    'hrl_gather_pad': (C.c_int, [C.POINTER(HrlGatherArgs), C.c_void_p]),
+    'hrl_last_error': (C.c_char_p, []),
+    'hrl_abi_version': (C.c_int32, []),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class HrlError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the CUDA library; raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise HrlError('handyrl_b200: %s is missing -- run `python -c "import __graft_entry__ as g; g.build()"` '
+                           '(there is no CPU or PyTorch fallback for the learner hot path)' % LIB_PATH)
+        h = C.CDLL(LIB_PATH)
+        for name, (res, argt) in SYMBOLS.items():
+            fn = getattr(h, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = argt
+        if h.hrl_abi_version() != HRL_ABI_VERSION:
+            raise HrlError('handyrl_b200: ABI mismatch (library %d, binding %d)' % (h.hrl_abi_version(), HRL_ABI_VERSION))
+        _lib = h
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise HrlError('hrl_b200 error %d: %s' % (status, lib().hrl_last_error().decode()))

@@ -1,0 +1,121 @@
+"""Seeded synthetic replay batches in the reference's batch-dict format.
+
+The layout is the one `make_batch` emits (reference handyrl/train.py:114-124):
+every tensor is (B, T, P-or-Pa, ...) batch-major, fp32 except `action` (int64).
+The recipe is the one written down in SURVEY.md section 8(d) so that the bench, the
+parity tests and the golden-vector generator all draw the same data.
+
+Nothing here touches the GPU; callers move the dict with `.to(device)`.
+"""
+
+import torch
+
+
+def synthetic_batch(B, T, P, A, *, turn_based=True, observation=False, reward_kind='zero',
+                    gamma=0.8, seed=0, obs_shape=(3, 3, 3), burn_in=0, with_obs=True):
+    """Build one replay batch.
+
+    turn_based & not observation -> Pa = 1 (turn-alternating layout, train.py:65-66)
+    otherwise                    -> Pa = P
+    reward_kind: 'zero' (TicTacToe-like) or 'step' (-0.01 per step, Geister-like geister.py:436-438)
+    burn_in > 0 also draws a random number of front-padded steps (train.py:94).
+    """
+    g = torch.Generator().manual_seed(seed)
+    Pa = 1 if (turn_based and not observation) else P
+
+    def randint(lo, hi, shape):  # inclusive bounds
+        return torch.randint(lo, hi + 1, shape, generator=g)
+
+    length = randint(max(1, T // 2), T, (B,))
+    front = randint(0, burn_in, (B,)) if burn_in > 0 else torch.zeros(B, dtype=torch.long)
+    length = torch.minimum(length, T - front)
+    t_idx = torch.arange(T).unsqueeze(0)
+    live = (t_idx >= front.unsqueeze(1)) & (t_idx < (front + length).unsqueeze(1))     # (B,T)
+    emask = live.float()
+
+    if turn_based:
+        first = randint(0, P - 1, (B,))
+        turn = (t_idx + first.unsqueeze(1)) % P                                          # (B,T)
+        tmask = torch.nn.functional.one_hot(turn, P).float() * emask.unsqueeze(-1)       # (B,T,P)
+    else:
+        tmask = emask.unsqueeze(-1).expand(B, T, P).clone()
+    omask = emask.unsqueeze(-1).expand(B, T, P).clone() if observation else tmask.clone()
+
+    # which policy rows carry a real decision
+    if Pa == 1:
+        row_live = live.unsqueeze(-1)                                                    # (B,T,1)
+    else:
+        row_live = tmask > 0                                                             # (B,T,P)
+
+    legal = torch.rand((B, T, Pa, A), generator=g) < 0.7
+    legal[..., 0] = True
+    legal = legal & row_live.unsqueeze(-1)
+    amask = (~legal).float() * 1e32
+
+    # uniform draw among the legal actions; 0 on dead rows
+    score = torch.rand((B, T, Pa, A), generator=g) - (~legal).float() * 2.0
+    action = score.argmax(-1)
+    action = torch.where(row_live, action, torch.zeros_like(action))
+
+    prob = torch.rand((B, T, Pa), generator=g).clamp(0.05, 1.0)
+    prob = torch.where(row_live, prob, torch.ones_like(prob))
+
+    if P == 2:
+        o = randint(-1, 1, (B,)).float()
+        outcome = torch.stack([o, -o], dim=1)
+    else:
+        outcome = randint(-1, 1, (B, P)).float()
+
+    value = torch.tanh(torch.randn((B, T, P), generator=g)) * omask
+    ended = t_idx >= (front + length).unsqueeze(1)
+    value = torch.where(ended.unsqueeze(-1), outcome.unsqueeze(1).expand(B, T, P), value)
+
+    if reward_kind == 'zero':
+        reward = torch.zeros(B, T, P)
+        ret = torch.zeros(B, T, P)
+    else:
+        reward = -0.01 * emask.unsqueeze(-1).expand(B, T, P).clone()
+        ret = torch.zeros(B, T, P)
+        acc = torch.zeros(B, P)
+        for t in range(T - 1, -1, -1):
+            acc = reward[:, t] + gamma * acc
+            ret[:, t] = acc
+        ret = ret * emask.unsqueeze(-1)
+
+    step = (t_idx - front.unsqueeze(1)).clamp(min=0).float()
+    progress = torch.where(live, step / length.unsqueeze(1).float(), torch.ones(B, T))
+
+    batch = {
+        'selected_prob': prob.unsqueeze(-1).contiguous(),
+        'value': value.unsqueeze(-1).contiguous(),
+        'action': action.unsqueeze(-1).contiguous(),
+        'outcome': outcome.view(B, 1, P, 1).contiguous(),
+        'reward': reward.unsqueeze(-1).contiguous(),
+        'return': ret.unsqueeze(-1).contiguous(),
+        'episode_mask': emask.view(B, T, 1, 1).contiguous(),
+        'turn_mask': tmask.unsqueeze(-1).contiguous(),
+        'observation_mask': omask.unsqueeze(-1).contiguous(),
+        'action_mask': amask.contiguous(),
+        'progress': progress.unsqueeze(-1).contiguous(),
+    }
+    if with_obs:
+        obs = (torch.rand((B, T, Pa) + tuple(obs_shape), generator=g) < 0.3).float()
+        batch['observation'] = obs * row_live.view(B, T, Pa, *([1] * len(obs_shape))).float()
+    return batch
+
+
+def synthetic_outputs(batch, *, has_value=True, has_return=False, seed=1):
+    """Raw net outputs for kernel-only tests: policy ~ N(0,1), value = tanh(N(0,1))."""
+    g = torch.Generator().manual_seed(seed)
+    B, T, Pa, A = batch['action_mask'].shape
+    out = {'policy': torch.randn((B, T, Pa, A), generator=g)}
+    if has_value:
+        out['value'] = torch.tanh(torch.randn((B, T, Pa, 1), generator=g))
+    if has_return:
+        out['return'] = 0.5 * torch.randn((B, T, Pa, 1), generator=g)
+    return out
+
+
+def bytes_per_cell(P, Pa, A, T, R):
+    """Algorithmic bytes of the fused loss pass per (b,t) cell, SURVEY.md 8(d)."""
+    return 12 * Pa * A + Pa * (20 + 8 * R) + 16 * P + 8 + 4.0 * P / T

@@ -1,0 +1,213 @@
+/*
+ * hrl_b200.h -- C ABI of the B200-native HandyRL learner hot path.
+ *
+ * The reference (DeNA/HandyRL) is pure Python and has no FFI layer; the seam this
+ * header introduces is the operator level underneath these reference functions:
+ *
+ *   hrl_loss_fwd_bwd      <- handyrl/train.py:176-184 (mask epilogue of forward_prediction)
+ *                            handyrl/train.py:218-267 (compute_loss)
+ *                            handyrl/train.py:189-215 (compose_losses)
+ *                            handyrl/losses.py:16-80  (monte_carlo / temporal_difference / upgo / vtrace)
+ *                            + the autograd pass of train.py:369 restricted to those ops
+ *   hrl_compute_target    <- handyrl/losses.py:63-80  (compute_target, stand-alone)
+ *   hrl_grad_sumsq /
+ *   hrl_clip_adam_step    <- handyrl/train.py:370-371 (clip_grad_norm_(params, 4.0) + Adam.step,
+ *                            Adam(lr, weight_decay=1e-5) of train.py:331)
+ *   hrl_gather_pad        <- handyrl/train.py:33-124  (make_batch: window slice + pad + collate)
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a DEVICE pointer unless stated;
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library allocates nothing;
+ *   - kernels are enqueued on the stream handed in (a cudaStream_t passed as void*), no
+ *     internal synchronisation, safe to capture in a CUDA graph;
+ *   - return value 0 = success, negative = HrlStatus error; hrl_last_error() gives the text
+ *     for the calling thread.  Nothing throws across this boundary.
+ *   - tensors are contiguous, batch-major exactly as make_batch emits them
+ *     (B, T, P|Pa, ...) fp32, `action` int64 (train.py:44-45, 111-124).
+ */
+#ifndef HRL_B200_H_
+#define HRL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRL_ABI_VERSION 1
+
+typedef enum {
+    HRL_OK = 0,
+    HRL_ERR_BAD_ARG = -1,      /* null pointer, bad dimension, unknown algorithm id        */
+    HRL_ERR_WORKSPACE = -2,    /* workspace missing or smaller than hrl_*_workspace_bytes   */
+    HRL_ERR_UNSUPPORTED = -3,  /* shape outside what the kernels were built for             */
+    HRL_ERR_CUDA = -4          /* a CUDA runtime call failed; see hrl_last_error()          */
+} HrlStatus;
+
+/* target algorithms, the strings of config.yaml `policy_target` / `value_target`
+ * (reference config.yaml:26-27, losses.py:68-78) */
+typedef enum { HRL_MC = 0, HRL_TD = 1, HRL_UPGO = 2, HRL_VTRACE = 3 } HrlAlgo;
+
+/* index of each reduced scalar in HrlLossArgs.losses */
+enum { HRL_LOSS_P = 0, HRL_LOSS_V = 1, HRL_LOSS_R = 2, HRL_LOSS_ENT = 3, HRL_LOSS_TOTAL = 4,
+       HRL_LOSS_DCNT = 5, HRL_NUM_LOSS = 6 };
+
+/*
+ * One fused forward+backward pass of the loss over a replay batch.
+ *
+ * Dimensions: B windows, T = burn_in + forward steps, P players on the value side,
+ * Pa players on the policy side (1 for the turn-alternating layout, else P; train.py:65-68),
+ * A actions.  Steps t < burn_in are excluded from every loss term and receive zero
+ * gradients (train.py:220-222).
+ */
+typedef struct HrlLossArgs {
+    int32_t B, T, P, Pa, A;
+    int32_t burn_in;
+    int32_t value_target;        /* HrlAlgo, used for targets (train.py:257-258)            */
+    int32_t policy_target;       /* HrlAlgo, used for advantages (train.py:260-262)         */
+    int32_t two_player_zero_sum; /* turn_based_training && P == 2 (train.py:243)            */
+    float lambda;                /* args['lambda']                                           */
+    float gamma;                 /* args['gamma'] (return stream; the value stream uses 1)   */
+    float entropy_regularization;
+    float entropy_regularization_decay;
+
+    /* raw net outputs (before the mask epilogue) */
+    const float *policy_raw;     /* (B,T,Pa,A)                                               */
+    const float *value_raw;      /* (B,T,Pa)   or NULL when the net has no value head        */
+    const float *return_raw;     /* (B,T,Pa)   or NULL when the net has no return head       */
+
+    /* replay batch */
+    const float *action_mask;    /* (B,T,Pa,A) 0 legal / 1e32 illegal                        */
+    const int64_t *action;       /* (B,T,Pa)                                                 */
+    const float *selected_prob;  /* (B,T,Pa)   behaviour probability                         */
+    const float *reward;         /* (B,T,P)                                                  */
+    const float *ret;            /* (B,T,P)    batch['return']                               */
+    const float *turn_mask;      /* (B,T,P)                                                  */
+    const float *observation_mask; /* (B,T,P)                                                */
+    const float *episode_mask;   /* (B,T)                                                    */
+    const float *progress;       /* (B,T)                                                    */
+    const float *outcome;        /* (B,P)                                                    */
+
+    /* outputs */
+    float *dpolicy_raw;          /* (B,T,Pa,A) d total / d policy_raw                        */
+    float *dvalue_raw;           /* (B,T,Pa)   or NULL iff value_raw is NULL                 */
+    float *dreturn_raw;          /* (B,T,Pa)   or NULL iff return_raw is NULL                */
+    float *losses;               /* [HRL_NUM_LOSS] p, v, r, ent, total, dcnt (sums)          */
+
+    /* optional per-element taps for parity tests; each may be NULL */
+    float *tap_target_value;     /* (B,T,P) targets['value']  (t >= burn_in, 0 before)       */
+    float *tap_target_return;    /* (B,T,P) targets['return']                                */
+    float *tap_advantage;        /* (B,T,P) total_advantages broadcast to P (train.py:265)   */
+    float *tap_logp;             /* (B,T,Pa) log pi(a) * episode_mask (train.py:232)         */
+    float *tap_rho;              /* (B,T,Pa) clipped importance ratio (train.py:237)         */
+    float *tap_entropy;          /* (B,T,Pa) policy entropy per row (train.py:208)           */
+
+    void *workspace;             /* >= hrl_loss_workspace_bytes(...) bytes, 256-byte aligned;
+                                    its first 64 bytes must be zero on the first call and are
+                                    left zero by every call                                  */
+    size_t workspace_bytes;
+} HrlLossArgs;
+
+/* Bytes of workspace hrl_loss_fwd_bwd needs for these dimensions (host call, no GPU work). */
+size_t hrl_loss_workspace_bytes(int32_t B, int32_t T, int32_t P, int32_t Pa, int32_t A);
+
+/* Enqueue the fused loss pass.  `stream` is a cudaStream_t. */
+int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream);
+
+/*
+ * Stand-alone compute_target (losses.py:63-80) on (B,T,P) columns.
+ *   values   (B,T,P) or NULL  -> targets = advantages = returns (losses.py:64-66)
+ *   returns  (B,Tr,P) with Tr == T or Tr == 1 (the (B,1,P,1) outcome of train.py:254)
+ *   rewards  (B,T,P) or NULL (= 0)
+ *   rhos, cs (B,T,Pr) with Pr == P or Pr == 1 (broadcast over players)
+ *   masks    (B,T,P)
+ *   targets, advantages (B,T,P) outputs
+ */
+int hrl_compute_target(int32_t algo, int32_t B, int32_t T, int32_t P, int32_t Tr, int32_t Pr,
+                       const float *values, const float *returns, const float *rewards,
+                       float lambda, float gamma, const float *rhos, const float *cs,
+                       const float *masks, float *targets, float *advantages, void *stream);
+
+/*
+ * Optimiser step on one flat fp32 parameter bucket (train.py:370-371).
+ *
+ * hrl_grad_sumsq writes per-block partial sums of grad^2 into `partials`
+ * (hrl_sumsq_num_partials() floats); hrl_clip_adam_step reduces them in a fixed order,
+ * applies clip_grad_norm_(max_norm) and one Adam step with L2 weight decay
+ * (torch.optim.Adam semantics: grad += wd * param before the moments).
+ *
+ * `lr` and `step` live on the device so that a captured CUDA graph stays valid while
+ * the learner changes the learning rate every epoch (train.py:383-384); the kernel
+ * increments *step.
+ */
+int32_t hrl_sumsq_num_partials(void);
+int hrl_grad_sumsq(const float *grad, int64_t n, float *partials, void *stream);
+int hrl_clip_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
+                       int64_t n, const float *partials, const float *lr, int64_t *step,
+                       float max_norm, float beta1, float beta2, float eps, float weight_decay,
+                       float *grad_norm_out /* may be NULL */, void *stream);
+
+/*
+ * Replay gather/pad: the device form of make_batch (train.py:33-124).
+ *
+ * Episodes are kept decoded in flat device arrays ("replay store"), one row per step:
+ *   per step s and player p (value side, Ps players):  obs_mask, turn_mask(=selected_prob present),
+ *   selected_prob, action, value, reward, return; per step: action_mask rows, observation rows.
+ * A window descriptor selects [start, end) of one episode and where it lands in [0, T).
+ */
+typedef struct HrlWindow {
+    int64_t first_step;   /* row of the episode's step 0 in the store                          */
+    int32_t start, end;   /* window [start, end) in episode steps (train.py:305-306)           */
+    int32_t train_start;  /* first trained step (train.py:304); pad_before = burn_in-(train_start-start) */
+    int32_t total;        /* episode length, for progress = step / total (train.py:89)        */
+    int32_t outcome_row;  /* row in the store's outcome table                                  */
+    int32_t reserved;
+} HrlWindow;
+
+typedef struct HrlGatherArgs {
+    int32_t B, T, P, Pa, A;
+    int32_t burn_in;
+    int32_t obs_elems;            /* floats per observation (flattened leaf)                   */
+    int32_t turn_alternating;     /* Pa == 1 layout: pick the turn player's row (train.py:65-66) */
+    const HrlWindow *windows;     /* [B] device                                                */
+
+    /* replay store, S = total stored steps */
+    const float *st_obs;          /* (S,P,obs_elems) zero where the player did not observe     */
+    const float *st_prob;         /* (S,P)  1.0 where absent                                   */
+    const int32_t *st_action;     /* (S,P)  0 where absent                                     */
+    const float *st_amask;        /* (S,P,A) 1e32 where absent                                 */
+    const float *st_value;        /* (S,P)                                                     */
+    const float *st_reward;       /* (S,P)                                                     */
+    const float *st_return;       /* (S,P)                                                     */
+    const uint8_t *st_flags;      /* (S,P) bit0 = acted (turn_mask), bit1 = observed           */
+    const int32_t *st_turn;       /* (S)   first turn player of the step (train.py:66)         */
+    const float *st_outcome;      /* (E,P)                                                     */
+
+    /* batch outputs, layouts of train.py:114-124 */
+    float *observation;           /* (B,T,Pa,obs_elems)                                        */
+    float *selected_prob;         /* (B,T,Pa)                                                  */
+    float *value;                 /* (B,T,P)                                                   */
+    int64_t *action;              /* (B,T,Pa)                                                  */
+    float *outcome;               /* (B,P)                                                     */
+    float *reward;                /* (B,T,P)                                                   */
+    float *ret;                   /* (B,T,P)                                                   */
+    float *episode_mask;          /* (B,T)                                                     */
+    float *turn_mask;             /* (B,T,P)                                                   */
+    float *observation_mask;      /* (B,T,P)                                                   */
+    float *action_mask;           /* (B,T,Pa,A)                                                */
+    float *progress;              /* (B,T)                                                     */
+} HrlGatherArgs;
+
+int hrl_gather_pad(const HrlGatherArgs *args, void *stream);
+
+/* Text of the last error raised on the calling thread ("" if none). */
+const char *hrl_last_error(void);
+
+/* HRL_ABI_VERSION the library was built with. */
+int32_t hrl_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRL_B200_H_ */
