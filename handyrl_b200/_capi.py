@@ -43,13 +43,13 @@ class HrlLossArgs(C.Structure):
 class HrlWindow(C.Structure):
     _fields_ = [('first_step', C.c_int64), ('start', C.c_int32), ('end', C.c_int32),
                 ('train_start', C.c_int32), ('total', C.c_int32), ('outcome_row', C.c_int32),
-                ('reserved', C.c_int32)]
+                ('player', C.c_int32)]
 
 
 class HrlGatherArgs(C.Structure):
     _fields_ = [
         ('B', C.c_int32), ('T', C.c_int32), ('P', C.c_int32), ('Pa', C.c_int32), ('A', C.c_int32),
-        ('burn_in', C.c_int32), ('obs_elems', C.c_int32), ('turn_alternating', C.c_int32),
+        ('Ps', C.c_int32), ('burn_in', C.c_int32), ('obs_elems', C.c_int32), ('turn_alternating', C.c_int32),
         ('windows', C.c_void_p),
         ('st_obs', C.c_void_p), ('st_prob', C.c_void_p), ('st_action', C.c_void_p), ('st_amask', C.c_void_p),
         ('st_value', C.c_void_p), ('st_reward', C.c_void_p), ('st_return', C.c_void_p),
@@ -70,7 +70,7 @@ SYMBOLS = {
     'hrl_sumsq_num_partials': (C.c_int32, []),
     'hrl_grad_sumsq': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'hrl_clip_adam_step': (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 3 +
-                           [C.c_float] * 5 + [C.c_void_p, C.c_void_p]),
+                           [C.c_double] * 5 + [C.c_void_p, C.c_void_p]),
     'hrl_gather_pad': (C.c_int, [C.POINTER(HrlGatherArgs), C.c_void_p]),
     'hrl_last_error': (C.c_char_p, []),
     'hrl_abi_version': (C.c_int32, []),

@@ -1,0 +1,201 @@
+"""Thin Python front end of the C ABI: torch tensors in, torch tensors out.
+
+torch is used for device memory and streams only; every computation happens in the
+CUDA library (handyrl_b200/libhrl_b200.so, sources in handyrl_b200/csrc/).  There is no
+fallback path: a CPU tensor or a missing library raises.
+"""
+import ctypes as C
+
+import torch
+
+from . import _capi
+from ._capi import ALGO_ID, LOSS_KEYS, NUM_LOSS, HrlLossArgs, check, lib
+
+_workspaces = {}
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f32(t, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _capi.HrlError('handyrl_b200: %s must be a CUDA tensor (no CPU path exists)' % name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _workspace(nbytes, device):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def algo_id(name):
+    try:
+        return ALGO_ID[name]
+    except KeyError:
+        # the reference prints 'No algorithm named ...' and returns None (losses.py:79-80)
+        raise ValueError('No algorithm named %s' % name)
+
+
+class LossBuffers:
+    """Pre-allocated outputs of one fused loss launch (re-used across steps / graph replays)."""
+
+    def __init__(self, B, T, P, Pa, A, has_value, has_return, device, taps=False):
+        f = dict(dtype=torch.float32, device=device)
+        self.dims = (B, T, P, Pa, A)
+        self.dpolicy = torch.empty((B, T, Pa, A), **f)
+        self.dvalue = torch.empty((B, T, Pa, 1), **f) if has_value else None
+        self.dreturn = torch.empty((B, T, Pa, 1), **f) if has_return else None
+        self.losses = torch.zeros(NUM_LOSS, **f)
+        self.taps = None
+        if taps:
+            self.taps = {
+                'target_value': torch.zeros((B, T, P, 1), **f), 'target_return': torch.zeros((B, T, P, 1), **f),
+                'advantage': torch.zeros((B, T, P, 1), **f), 'logp': torch.zeros((B, T, Pa, 1), **f),
+                'rho': torch.zeros((B, T, Pa, 1), **f), 'entropy': torch.zeros((B, T, Pa), **f),
+            }
+        self.workspace = torch.zeros(lib().hrl_loss_workspace_bytes(B, T, P, Pa, A), dtype=torch.uint8, device=device)
+
+
+def loss_fwd_bwd(outputs, batch, args, buffers=None, taps=False):
+    """Fused mask epilogue + compute_loss + closed-form backward (reference train.py:176-267).
+
+    outputs: raw net outputs {'policy': (B,T,Pa,A), 'value': (B,T,Pa,1)?, 'return': (B,T,Pa,1)?}
+    batch:   the make_batch dict (device tensors)
+    args:    train_args (lambda, gamma, entropy_regularization[_decay], policy_target, value_target,
+             turn_based_training, burn_in_steps)
+    returns  LossBuffers with .losses = [p, v, r, ent, total, dcnt] and the gradients.
+    """
+    policy = _dev_f32(outputs['policy'], 'policy')
+    B, T, Pa, A = policy.shape
+    P = batch['turn_mask'].shape[2]
+    value = _dev_f32(outputs.get('value'), 'value')
+    ret_head = _dev_f32(outputs.get('return'), 'return')
+    if buffers is None:
+        buffers = LossBuffers(B, T, P, Pa, A, value is not None, ret_head is not None, policy.device, taps=taps)
+    assert buffers.dims == (B, T, P, Pa, A)
+
+    a = HrlLossArgs()
+    a.B, a.T, a.P, a.Pa, a.A = B, T, P, Pa, A
+    a.burn_in = int(args.get('burn_in_steps', 0))
+    a.value_target = algo_id(args['value_target'])
+    a.policy_target = algo_id(args['policy_target'])
+    a.two_player_zero_sum = int(bool(args['turn_based_training']) and P == 2)
+    a.lambda_ = float(args['lambda'])
+    a.gamma = float(args['gamma'])
+    a.entropy_regularization = float(args['entropy_regularization'])
+    a.entropy_regularization_decay = float(args['entropy_regularization_decay'])
+
+    action = batch['action']
+    if not action.is_cuda:
+        raise _capi.HrlError('handyrl_b200: the batch must live on the GPU')
+    keep = [policy, value, ret_head,
+            _dev_f32(batch['action_mask'], 'action_mask'), action.long().contiguous(),
+            _dev_f32(batch['selected_prob'], 'selected_prob'), _dev_f32(batch['reward'], 'reward'),
+            _dev_f32(batch['return'], 'return'), _dev_f32(batch['turn_mask'], 'turn_mask'),
+            _dev_f32(batch['observation_mask'], 'observation_mask'), _dev_f32(batch['episode_mask'], 'episode_mask'),
+            _dev_f32(batch['progress'], 'progress'), _dev_f32(batch['outcome'], 'outcome')]
+    (a.policy_raw, a.value_raw, a.return_raw, a.action_mask, a.action, a.selected_prob, a.reward, a.ret,
+     a.turn_mask, a.observation_mask, a.episode_mask, a.progress, a.outcome) = [_ptr(t) for t in keep]
+    a.dpolicy_raw, a.dvalue_raw, a.dreturn_raw = _ptr(buffers.dpolicy), _ptr(buffers.dvalue), _ptr(buffers.dreturn)
+    a.losses = _ptr(buffers.losses)
+    if buffers.taps is not None:
+        t = buffers.taps
+        a.tap_target_value, a.tap_target_return, a.tap_advantage = _ptr(t['target_value']), _ptr(t['target_return']), _ptr(t['advantage'])
+        a.tap_logp, a.tap_rho, a.tap_entropy = _ptr(t['logp']), _ptr(t['rho']), _ptr(t['entropy'])
+    a.workspace = _ptr(buffers.workspace)
+    a.workspace_bytes = buffers.workspace.numel()
+    check(lib().hrl_loss_fwd_bwd(C.byref(a), _stream_ptr()))
+    buffers._keep = keep  # the launch is asynchronous: keep temporaries alive
+    return buffers
+
+
+def compute_target(algorithm, values, returns, rewards, lmb, gamma, rhos, cs, masks):
+    """Drop-in for handyrl.losses.compute_target on CUDA tensors of shape (B,T,P,1)."""
+    aid = algo_id(algorithm)
+    returns = _dev_f32(returns, 'returns')
+    if values is None:  # losses.py:64-66
+        return returns, returns
+    values = _dev_f32(values, 'values')
+    B, T, P = values.shape[:3]
+    rewards, rhos, cs, masks = (_dev_f32(x, n) for x, n in ((rewards, 'rewards'), (rhos, 'rhos'), (cs, 'cs'), (masks, 'masks')))
+    if masks is not None and masks.shape[2] != P:
+        masks = masks.expand(B, T, P, 1).contiguous()
+    Tr = returns.shape[1]
+    if returns.shape[2] != P:
+        returns = returns.expand(B, Tr, P, 1).contiguous()
+    Pr = rhos.shape[2] if rhos is not None else 1
+    targets = torch.empty_like(values)
+    advantages = torch.empty_like(values)
+    check(lib().hrl_compute_target(aid, B, T, P, Tr, Pr, _ptr(values), _ptr(returns), _ptr(rewards), float(lmb),
+                                   float(gamma), _ptr(rhos), _ptr(cs), _ptr(masks), _ptr(targets), _ptr(advantages),
+                                   _stream_ptr()))
+    return targets, advantages
+
+
+class FlatAdam:
+    """clip_grad_norm_(max_norm) + Adam(weight_decay) on one flat fp32 bucket (train.py:331, 370-371).
+
+    The model's parameters are re-pointed into one contiguous buffer and their .grad into a
+    second one, so that (a) the multi-GPU gradient exchange is ONE all-reduce(SUM) and
+    (b) the whole optimiser step is two kernel launches.  `extra` floats are appended to the
+    gradient bucket (the learner puts the six loss scalars there so they ride the same
+    all-reduce).
+    """
+
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, max_norm=4.0, extra=0):
+        params = [p for p in params]
+        assert len(params) > 0 and all(p.is_cuda and p.dtype == torch.float32 for p in params)
+        self.params = params
+        device = params[0].device
+        self.n = sum(p.numel() for p in params)
+        n_pad = (self.n + 3) // 4 * 4
+        self.extra = extra
+        self.flat_param = torch.zeros(n_pad, dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros(n_pad + extra, dtype=torch.float32, device=device)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                self.flat_param[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat_param[off:off + k].view_as(p)
+                p.grad = self.flat_grad[off:off + k].view_as(p)
+                off += k
+        self.n_pad = n_pad
+        self.exp_avg = torch.zeros(n_pad, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(n_pad, dtype=torch.float32, device=device)
+        self.partials = torch.zeros(lib().hrl_sumsq_num_partials(), dtype=torch.float32, device=device)
+        self.lr = torch.full((1,), float(lr), dtype=torch.float32, device=device)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=device)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=device)
+        self.betas, self.eps, self.weight_decay, self.max_norm = betas, eps, weight_decay, max_norm
+
+    @property
+    def extra_slots(self):
+        return self.flat_grad[self.n_pad:]
+
+    def set_lr(self, lr):
+        self.lr.fill_(float(lr))
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def step(self):
+        s = _stream_ptr()
+        check(lib().hrl_grad_sumsq(_ptr(self.flat_grad), self.n_pad, _ptr(self.partials), s))
+        check(lib().hrl_clip_adam_step(_ptr(self.flat_param), _ptr(self.flat_grad), _ptr(self.exp_avg),
+                                       _ptr(self.exp_avg_sq), self.n_pad, _ptr(self.partials), _ptr(self.lr),
+                                       _ptr(self.step_count), self.max_norm, self.betas[0], self.betas[1], self.eps,
+                                       self.weight_decay, _ptr(self.grad_norm), s))

@@ -145,7 +145,7 @@ int32_t hrl_sumsq_num_partials(void);
 int hrl_grad_sumsq(const float *grad, int64_t n, float *partials, void *stream);
 int hrl_clip_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
                        int64_t n, const float *partials, const float *lr, int64_t *step,
-                       float max_norm, float beta1, float beta2, float eps, float weight_decay,
+                       double max_norm, double beta1, double beta2, double eps, double weight_decay,
                        float *grad_norm_out /* may be NULL */, void *stream);
 
 /*
@@ -162,27 +162,28 @@ typedef struct HrlWindow {
     int32_t train_start;  /* first trained step (train.py:304); pad_before = burn_in-(train_start-start) */
     int32_t total;        /* episode length, for progress = step / total (train.py:89)        */
     int32_t outcome_row;  /* row in the store's outcome table                                  */
-    int32_t reserved;
+    int32_t player;       /* solo training (train.py:57-58): the one store player batched; else 0 */
 } HrlWindow;
 
 typedef struct HrlGatherArgs {
     int32_t B, T, P, Pa, A;
+    int32_t Ps;                   /* players per step in the store (P == Ps, or P == 1 for solo) */
     int32_t burn_in;
     int32_t obs_elems;            /* floats per observation (flattened leaf)                   */
     int32_t turn_alternating;     /* Pa == 1 layout: pick the turn player's row (train.py:65-66) */
     const HrlWindow *windows;     /* [B] device                                                */
 
     /* replay store, S = total stored steps */
-    const float *st_obs;          /* (S,P,obs_elems) zero where the player did not observe     */
-    const float *st_prob;         /* (S,P)  1.0 where absent                                   */
-    const int32_t *st_action;     /* (S,P)  0 where absent                                     */
-    const float *st_amask;        /* (S,P,A) 1e32 where absent                                 */
-    const float *st_value;        /* (S,P)                                                     */
-    const float *st_reward;       /* (S,P)                                                     */
-    const float *st_return;       /* (S,P)                                                     */
-    const uint8_t *st_flags;      /* (S,P) bit0 = acted (turn_mask), bit1 = observed           */
-    const int32_t *st_turn;       /* (S)   first turn player of the step (train.py:66)         */
-    const float *st_outcome;      /* (E,P)                                                     */
+    const float *st_obs;          /* (S,Ps,obs_elems) zero where the player did not observe     */
+    const float *st_prob;         /* (S,Ps) 1.0 where absent                                   */
+    const int32_t *st_action;     /* (S,Ps) 0 where absent                                     */
+    const float *st_amask;        /* (S,Ps,A) 1e32 where absent                                 */
+    const float *st_value;        /* (S,Ps)                                                    */
+    const float *st_reward;       /* (S,Ps)                                                    */
+    const float *st_return;       /* (S,Ps)                                                    */
+    const uint8_t *st_flags;      /* (S,Ps) bit0 = acted (turn_mask), bit1 = observed           */
+    const int32_t *st_turn;       /* (S)   index of the step's first turn player (train.py:66)         */
+    const float *st_outcome;      /* (E,Ps)                                                    */
 
     /* batch outputs, layouts of train.py:114-124 */
     float *observation;           /* (B,T,Pa,obs_elems)                                        */
