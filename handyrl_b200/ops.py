@@ -12,6 +12,8 @@ from . import _capi
 from ._capi import ALGO_ID, LOSS_KEYS, NUM_LOSS, HrlLossArgs, check, lib
 
 _workspaces = {}
+_BATCH_KEYS = ('action_mask', 'action', 'selected_prob', 'reward', 'return', 'turn_mask', 'observation_mask',
+               'episode_mask', 'progress', 'outcome')
 
 
 def _stream_ptr():
@@ -87,6 +89,14 @@ def loss_fwd_bwd(outputs, batch, args, buffers=None, taps=False):
         buffers = LossBuffers(B, T, P, Pa, A, value is not None, ret_head is not None, policy.device, taps=taps)
     assert buffers.dims == (B, T, P, Pa, A)
 
+    # static buffers (CUDA-graph replays): the argument block of the previous call is still valid
+    key = (policy.data_ptr(), 0 if value is None else value.data_ptr(), 0 if ret_head is None else ret_head.data_ptr(),
+           id(args)) + tuple(batch[k].data_ptr() for k in _BATCH_KEYS)
+    cached = getattr(buffers, '_cached', None)
+    if cached is not None and cached[0] == key:
+        check(lib().hrl_loss_fwd_bwd(C.byref(cached[1]), _stream_ptr()))
+        return buffers
+
     a = HrlLossArgs()
     a.B, a.T, a.P, a.Pa, a.A = B, T, P, Pa, A
     a.burn_in = int(args.get('burn_in_steps', 0))
@@ -119,6 +129,11 @@ def loss_fwd_bwd(outputs, batch, args, buffers=None, taps=False):
     a.workspace_bytes = buffers.workspace.numel()
     check(lib().hrl_loss_fwd_bwd(C.byref(a), _stream_ptr()))
     buffers._keep = keep  # the launch is asynchronous: keep temporaries alive
+    if all(k is None or k is o for k, o in zip(keep[3:], (batch['action_mask'], batch['action'], batch['selected_prob'],
+                                                          batch['reward'], batch['return'], batch['turn_mask'],
+                                                          batch['observation_mask'], batch['episode_mask'],
+                                                          batch['progress'], batch['outcome']))):
+        buffers._cached = (key, a)   # only when no temporary copies were made
     return buffers
 
 

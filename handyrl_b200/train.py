@@ -1,0 +1,559 @@
+"""B200-native learner hot path behind the reference's Python surface.
+
+Same public names as handyrl/train.py for the path
+    Batcher.batch -> forward_prediction -> compute_loss -> backward -> optimizer.step
+(reference train.py:127-400), different machinery:
+
+  * the net runs ONCE per step and returns raw outputs; the mask epilogue, the whole of
+    compute_loss / compose_losses / losses.py AND their backward run in one CUDA kernel
+    (ops.loss_fwd_bwd -> csrc/loss_kernel.cu) that hands autograd closed-form gradients;
+  * parameters and gradients live in one flat bucket: one NCCL all-reduce(SUM) per step when
+    sharded over GPUs, then clip+Adam in two launches (csrc/optim_kernel.cu);
+  * the whole step (H2D copies, net forward, loss kernel, net backward, all-reduce, optimiser)
+    is captured in a CUDA graph and replayed; the host never synchronises inside an epoch
+    (the reference does 4-6 .item() syncs per step, train.py:200, 375-376).
+"""
+import copy
+import queue
+import random
+import threading
+import time
+from collections import deque
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .batch import tree_map, tree_leaves, make_batch, flatten_moments, decode_moments, gather_windows, sample_window
+from ._capi import LOSS_KEYS, NUM_LOSS
+
+
+# --------------------------------------------------------------------------- forward
+
+def _call_model(model, obs, hidden):
+    return model(obs, hidden)
+
+
+def forward_raw(model, hidden, batch, args):
+    """Run the net over a batch and return its RAW outputs shaped (B, T, Pa, ...).
+
+    Feed-forward nets see all B*T*Pa observations at once; recurrent nets are stepped over T
+    with the hidden state masked by observation_mask, burn-in steps without gradient and in
+    eval mode, exactly as the reference does (train.py:142-174) -- but WITHOUT the mask
+    epilogue of train.py:176-184, which the fused loss kernel applies on the fly.
+    """
+    observations = batch['observation']
+    B, T, Pa = batch['action'].shape[:3]
+
+    if hidden is None:
+        flat = tree_map(lambda o: o.flatten(0, 2), observations)
+        outs = _call_model(model, flat, None)
+        return {k: v.unflatten(0, (B, T, Pa)) for k, v in outs.items() if k != 'hidden' and v is not None}
+
+    alternating = args['turn_based_training'] and not args['observation']
+    burn_in = args['burn_in_steps']
+    per_step = {}
+    omask_all = batch['observation_mask']
+    for t in range(T):
+        obs_t = tree_map(lambda o: o[:, t].flatten(0, 1), observations)
+        om = omask_all[:, t]                                                   # (B, P, 1)
+
+        def gate(h):
+            return om.view(*h.shape[:2], *([1] * (h.dim() - 2)))
+
+        visible = tree_map(lambda h: h * gate(h), hidden)
+        if alternating:
+            visible = tree_map(lambda h: h.sum(1), visible)                    # only the turn player observes
+        else:
+            visible = tree_map(lambda h: h.flatten(0, 1), visible)
+        if t < burn_in:
+            model.eval()
+            with torch.no_grad():
+                out_t = _call_model(model, obs_t, visible)
+        else:
+            if not model.training:
+                model.train()
+            out_t = _call_model(model, obs_t, visible)
+        new_hidden = out_t.pop('hidden', None)
+        for k, v in out_t.items():
+            if v is not None:
+                per_step.setdefault(k, []).append(v.unflatten(0, (B, Pa)))
+        new_hidden = tree_map(lambda h: h.unflatten(0, (B, Pa)), new_hidden)
+        hidden = tree_map(lambda h, nh: h * (1 - gate(h)) + nh * gate(h), hidden, new_hidden)
+    return {k: torch.stack(v, dim=1) for k, v in per_step.items()}
+
+
+def forward_prediction(model, hidden, batch, args):
+    """API-compatible with handyrl.train.forward_prediction: raw outputs + the mask epilogue
+    (train.py:176-184) as torch ops.  NOT used by the learner below (the epilogue is fused into
+    the loss kernel); kept so code written against the reference keeps importing."""
+    outs = forward_raw(model, hidden, batch, args)
+    Pa = batch['action'].shape[2]
+    masked = {}
+    for k, o in outs.items():
+        if k == 'policy':
+            o = o * batch['turn_mask']
+            if o.size(2) > 1 and Pa == 1:
+                o = o.sum(2, keepdim=True)
+            masked[k] = o - batch['action_mask']
+        else:
+            masked[k] = o * batch['observation_mask']
+    return masked
+
+
+# --------------------------------------------------------------------------- loss
+
+class _FusedLoss(torch.autograd.Function):
+    """total = fused_loss(policy_raw, value_raw?, return_raw?); backward returns the closed-form
+    gradients the kernel already produced, scaled by grad_output."""
+
+    @staticmethod
+    def forward(ctx, batch, args, keys, *heads):
+        outs = dict(zip(keys, [h.detach() for h in heads]))
+        buf = ops.loss_fwd_bwd(outs, batch, args)
+        grads = {'policy': buf.dpolicy, 'value': buf.dvalue, 'return': buf.dreturn}
+        ctx.save_for_backward(*[grads[k] for k in keys])
+        ctx.mark_non_differentiable(buf.losses)
+        total = buf.losses[4].clone()
+        return total, buf.losses
+
+    @staticmethod
+    def backward(ctx, g_total, _g_losses):
+        return (None, None, None) + tuple(g * g_total for g in ctx.saved_tensors)
+
+
+def compute_loss(batch, model, hidden, args):
+    """Drop-in for handyrl.train.compute_loss (train.py:218-267): returns
+    ({'p','v','r','ent','total'} 0-d tensors, dcnt float).  `total` is differentiable."""
+    outs = forward_raw(model, hidden, batch, args)
+    keys = [k for k in ('policy', 'value', 'return') if k in outs]
+    total, vec = _FusedLoss.apply(batch, args, keys, *[outs[k] for k in keys])
+    losses = {'p': vec[0]}
+    if 'value' in outs:
+        losses['v'] = vec[1]
+    if 'return' in outs:
+        losses['r'] = vec[2]
+    losses['ent'] = vec[3]
+    losses['total'] = total
+    return losses, float(vec[5].item())     # the reference also synchronises here (train.py:200)
+
+
+# --------------------------------------------------------------------------- one learner step
+
+def _align(x, a=256):
+    return (x + a - 1) // a * a
+
+
+class BatchLayout:
+    """Byte layout of one replay batch packed into a single buffer (one H2D copy per step).
+    `value` (the behaviour value, train.py:117) is left out: nothing on the hot path reads it."""
+
+    SKIP = ('value',)
+
+    def __init__(self, example_batch):
+        self.entries = []      # (key path tuple, shape, dtype, offset)
+        off = 0
+
+        def walk(tree, path):
+            nonlocal off
+            if isinstance(tree, dict):
+                for k, v in tree.items():
+                    walk(v, path + (k,))
+            elif isinstance(tree, (list, tuple)):
+                for i, v in enumerate(tree):
+                    walk(v, path + (i,))
+            else:
+                self.entries.append((path, tuple(tree.shape), tree.dtype, off))
+                off = _align(off + tree.numel() * tree.element_size())
+
+        for k, v in example_batch.items():
+            if k not in self.SKIP:
+                walk(v, (k,))
+        self.template = {k: v for k, v in example_batch.items() if k not in self.SKIP}
+        self.nbytes = off
+        self.payload_bytes = sum(int(torch.tensor(sh).prod()) * torch.empty(0, dtype=dt).element_size()
+                                 for _, sh, dt, _ in self.entries)
+
+    def views(self, buf):
+        """Tree of tensors (same nesting as the batch) aliasing the flat uint8 buffer `buf`."""
+        flat = {}
+        for path, shape, dtype, off in self.entries:
+            n = int(torch.tensor(shape).prod()) * torch.empty(0, dtype=dtype).element_size()
+            flat[path] = buf[off:off + n].view(dtype).view(shape)
+
+        def build(tree, path):
+            if isinstance(tree, dict):
+                return type(tree)((k, build(v, path + (k,))) for k, v in tree.items())
+            if isinstance(tree, (list, tuple)):
+                return type(tree)(build(v, path + (i,)) for i, v in enumerate(tree))
+            return flat[path]
+
+        return build(self.template, ())
+
+
+class PackedBatch:
+    """A replay batch in ONE pinned host buffer; `tensors` alias it in the reference's dict layout."""
+
+    def __init__(self, layout):
+        self.layout = layout
+        self.buffer = torch.empty(layout.nbytes, dtype=torch.uint8).pin_memory()
+        self.tensors = layout.views(self.buffer)
+        self.in_flight = None      # CUDA event: the H2D copy reading this buffer has completed
+
+    def fill(self, host_batch):
+        for d, s in zip(tree_leaves(self.tensors), tree_leaves({k: host_batch[k] for k in self.tensors})):
+            d.copy_(s)
+        return self
+
+    def wait_reusable(self):
+        if self.in_flight is not None:
+            self.in_flight.synchronize()
+            self.in_flight = None
+
+
+class LearnerStep:
+    """One replay batch -> one optimiser step.
+
+    step(packed):  ONE H2D copy of the packed pinned batch -> [CUDA graph: net forward ->
+    fused loss fwd+bwd kernel -> net backward -> (all-reduce SUM) -> clip + Adam].
+    The six loss sums land in `last_losses` / `loss_accum` on the device; nothing in here
+    synchronises the host.
+    """
+
+    def __init__(self, model, args, example_batch, lr, device=None, process_group=None, use_graph=True,
+                 max_norm=4.0, weight_decay=1e-5, time_loss_kernel=False):
+        self.device = torch.device(device if device is not None else 'cuda')
+        self.args = args
+        self.model = model.to(self.device)
+        self.model.train()
+        self.time_loss_kernel = time_loss_kernel
+        self.kernel_events = []
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        params = [p for p in self.model.parameters()]
+        self.opt = ops.FlatAdam(params, lr=lr, weight_decay=weight_decay, max_norm=max_norm, extra=NUM_LOSS)
+
+        self.layout = BatchLayout(example_batch)
+        self.dev_buffer = torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=self.device)
+        self.dev = self.layout.views(self.dev_buffer)
+        self.h2d_bytes = self.layout.nbytes
+        B, T, Pa, A = example_batch['action_mask'].shape
+        P = example_batch['turn_mask'].shape[2]
+        self.dims = (B, T, P, Pa, A)
+        self.hidden0 = None
+        if hasattr(self.model, 'init_hidden'):
+            self.hidden0 = tree_map(lambda h: h.to(self.device), self.model.init_hidden([B, P]))
+        self.loss_buf = None
+        self.last_losses = torch.zeros(NUM_LOSS, device=self.device)
+        self.loss_accum = torch.zeros(NUM_LOSS, dtype=torch.float64, device=self.device)
+        self.host_slots = torch.zeros((8, NUM_LOSS)).pin_memory()
+        self._slot = 0
+        self.graph = None
+        self.use_graph = use_graph
+        self.steps = 0
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._warm = PackedBatch(self.layout).fill(example_batch)
+
+    # -- the device work of one step, on the current stream (inputs already in self.dev)
+    def _part_forward(self):
+        self.opt.zero_grad()
+        self._outs = forward_raw(self.model, self.hidden0, self.dev, self.args)
+        if self.loss_buf is None:
+            B, T, P, Pa, A = self.dims
+            self.loss_buf = ops.LossBuffers(B, T, P, Pa, A, 'value' in self._outs, 'return' in self._outs, self.device)
+
+    def _part_loss(self):
+        outs = self._outs
+        ops.loss_fwd_bwd({k: outs[k] for k in ('policy', 'value', 'return') if k in outs}, self.dev, self.args,
+                         buffers=self.loss_buf)
+
+    def _part_backward(self):
+        outs, buf = self._outs, self.loss_buf
+        heads, grads = [outs['policy']], [buf.dpolicy]
+        if 'value' in outs:
+            heads.append(outs['value'])
+            grads.append(buf.dvalue)
+        if 'return' in outs:
+            heads.append(outs['return'])
+            grads.append(buf.dreturn)
+        torch.autograd.backward(heads, grads)
+        self._outs = None
+        self.opt.extra_slots.copy_(buf.losses)            # the loss sums ride the gradient bucket
+        if self.world > 1:
+            torch.distributed.all_reduce(self.opt.flat_grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        self.opt.step()
+        self.last_losses.copy_(self.opt.extra_slots)
+        self.loss_accum.add_(self.last_losses)
+
+    def _device_step(self):
+        self._part_forward()
+        self._part_loss()
+        self._part_backward()
+
+    def _capture(self):
+        # warm-up on the step stream (cuDNN heuristics, lazy inits, NCCL communicator), then capture
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.dev_buffer.copy_(self._warm.buffer, non_blocking=True)
+            state = self._snapshot()
+            for _ in range(3):
+                self._device_step()
+            self.stream.synchronize()
+            self._restore(state)
+            if self.use_graph and not self.time_loss_kernel:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=self.stream):
+                    self._device_step()
+                self._restore(state)
+            elif self.use_graph:
+                # the loss kernel is launched between two graphs so that CUDA events can bracket it
+                self.graph_fwd = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_fwd, stream=self.stream):
+                    self._part_forward()
+                self._part_loss()
+                self.graph_bwd = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_bwd, pool=self.graph_fwd.pool(), stream=self.stream):
+                    self._part_backward()
+                self._restore(state)
+            self.stream.synchronize()
+        self._captured = True
+
+    def _snapshot(self):
+        bufs = {k: v.clone() for k, v in self.model.state_dict().items()}
+        return (bufs, self.opt.exp_avg.clone(), self.opt.exp_avg_sq.clone(), self.opt.step_count.clone(),
+                self.loss_accum.clone())
+
+    def _restore(self, state):
+        bufs, m, v, sc, acc = state
+        with torch.no_grad():
+            for k, t in self.model.state_dict().items():
+                t.copy_(bufs[k])
+            self.opt.exp_avg.copy_(m)
+            self.opt.exp_avg_sq.copy_(v)
+            self.opt.step_count.copy_(sc)
+            self.loss_accum.copy_(acc)
+
+    def new_packed(self):
+        return PackedBatch(self.layout)
+
+    def step(self, packed):
+        """Enqueue H2D + one learner step for a PackedBatch; returns without waiting for the GPU.
+        `packed.in_flight` tells when its host buffer may be refilled."""
+        self._enqueue(packed.buffer, packed)
+
+    def step_resident(self, dev_bytes):
+        """Same step with the packed batch already in HBM (e.g. produced by the replay gather kernel)."""
+        self._enqueue(dev_bytes, None)
+
+    def _enqueue(self, src_bytes, packed):
+        if not getattr(self, '_captured', False):
+            self._capture()
+        with torch.cuda.stream(self.stream):
+            self.dev_buffer.copy_(src_bytes, non_blocking=True)
+            if packed is not None:
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                packed.in_flight = ev
+            if not self.use_graph:
+                self._device_step()
+            elif not self.time_loss_kernel:
+                self.graph.replay()
+            else:
+                self.graph_fwd.replay()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self.stream)
+                self._part_loss()
+                e1.record(self.stream)
+                self.kernel_events.append((e0, e1))
+                self.graph_bwd.replay()
+        self.steps += 1
+
+    def loss_kernel_ms(self):
+        """Average device time of the fused loss kernel over the steps since the last call
+        (needs time_loss_kernel=True)."""
+        self.stream.synchronize()
+        ts = [a.elapsed_time(b) for a, b in self.kernel_events]
+        self.kernel_events = []
+        return sum(ts) / max(1, len(ts)), len(ts)
+
+    def fetch_losses_async(self):
+        """Enqueue the D2H copy of the last step's six loss sums (24 bytes) behind that step and
+        return a handle; handle() waits for just that copy and returns the dict."""
+        slot = self.host_slots[self._slot % self.host_slots.shape[0]]
+        self._slot += 1
+        with torch.cuda.stream(self.stream):
+            slot.copy_(self.last_losses, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+
+        def get():
+            ev.synchronize()
+            return dict(zip(LOSS_KEYS, slot.tolist()))
+        return get
+
+    def read_losses(self):
+        """Blocking read of the last step's six loss sums."""
+        return self.fetch_losses_async()()
+
+    def pop_accumulated(self):
+        """Loss sums accumulated since the last call (ONE host sync per epoch)."""
+        self.stream.synchronize()
+        vals = self.loss_accum.cpu().tolist()
+        self.loss_accum.zero_()
+        return dict(zip(LOSS_KEYS, vals))
+
+    def cpu_state_dict(self):
+        self.stream.synchronize()
+        return {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}
+
+
+# --------------------------------------------------------------------------- batcher + trainer
+
+class Batcher:
+    """Feeds the trainer: recency-biased window sampling (train.py:291-315) and collation.
+
+    Unlike the reference there is no process pool shipping pickled batches through pipes
+    (train.py:274, connection.py:133-173): episodes are decoded once into FlatEpisode arrays
+    (cached on the episode dict) and batches are built by `num_batchers` threads with numpy
+    gathers that release the GIL.
+    """
+
+    def __init__(self, args, episodes):
+        self.args = args
+        self.episodes = episodes
+        self.out = queue.Queue(maxsize=8)
+        self.threads = []
+        self.started = False
+
+    def select_episode(self):
+        idx, st, ed, tst = sample_window(lambda: len(self.episodes), lambda i: self.episodes[i]['steps'], self.args)
+        ep = self.episodes[idx]
+        cs = self.args['compress_steps']
+        b0, b1 = st // cs, (ed - 1) // cs + 1
+        return {'args': ep['args'], 'outcome': ep['outcome'], 'moment': ep['moment'][b0:b1], 'base': b0 * cs,
+                'start': st, 'end': ed, 'train_start': tst, 'total': ep['steps'], '_episode': ep}
+
+    @staticmethod
+    def _flat(ep):
+        fe = ep.get('_flat')
+        if fe is None:
+            fe = flatten_moments(decode_moments(ep['moment']), ep['outcome'])
+            ep['_flat'] = fe
+        return fe
+
+    def _make(self):
+        windows = []
+        for _ in range(self.args['batch_size']):
+            sel = self.select_episode()
+            fe = self._flat(sel['_episode'])
+            windows.append((fe, sel['start'], sel['end'], sel['start'], sel['train_start'], sel['total']))
+        nb = gather_windows(windows, self.args)
+        return tree_map(lambda a: torch.from_numpy(a), nb)
+
+    def _worker(self, bid):
+        print('started batcher %d' % bid)
+        while True:
+            self.out.put(self._make())
+
+    def run(self):
+        if self.started:
+            return
+        self.started = True
+        for i in range(self.args['num_batchers']):
+            th = threading.Thread(target=self._worker, args=(i,), daemon=True)
+            th.start()
+            self.threads.append(th)
+
+    def batch(self):
+        return self.out.get()
+
+
+class Trainer:
+    """Drop-in for handyrl.train.Trainer (train.py:321-400): same constructor, attributes
+    (`episodes`, `steps`), `run()` thread body and `update()` hand-off, same printed lines."""
+
+    def __init__(self, args, model):
+        self.episodes = deque()
+        self.args = args
+        self.model = model
+        self.default_lr = 3e-8
+        self.data_cnt_ema = self.args['batch_size'] * self.args['forward_steps']
+        self.params = list(self.model.parameters())
+        self.lr = self.default_lr * self.data_cnt_ema
+        self.steps = 0
+        self.batcher = Batcher(self.args, self.episodes)
+        self.update_flag = False
+        self.update_queue = queue.Queue(maxsize=1)
+        self.stepper = None
+        if len(self.params) > 0 and not torch.cuda.is_available():
+            raise RuntimeError('handyrl_b200.Trainer needs a CUDA device; there is no CPU learner in this package')
+
+    def update(self):
+        self.update_flag = True
+        model, steps = self.update_queue.get()
+        return model, steps
+
+    def _cpu_model(self):
+        self.cpu_template.load_state_dict(self.stepper.cpu_state_dict())
+        self.cpu_template.eval()
+        return copy.deepcopy(self.cpu_template)
+
+    def train(self):
+        if len(self.params) == 0:          # non-parametric model (train.py:348-350)
+            time.sleep(0.1)
+            return self.model
+        batch_cnt, data_cnt, loss_sum = 0, 0, {}
+        while True:
+            batch = self.batcher.batch()
+            if self.stepper is None:
+                self.cpu_template = copy.deepcopy(self.model)
+                self.stepper = LearnerStep(self.model, self.args, batch, self.lr)
+                self.batcher.pool = [self.stepper.new_packed() for _ in range(4)]
+            packed = self.batcher.pool[batch_cnt % len(self.batcher.pool)]
+            packed.wait_reusable()
+            packed.fill(batch)
+            self.stepper.step(packed)
+            batch_cnt += 1
+            self.steps += 1
+            if self.update_flag:            # ONE host sync per epoch instead of 4-6 per step
+                acc = self.stepper.pop_accumulated()
+                data_cnt += acc.pop('dcnt')
+                for k, v in acc.items():
+                    loss_sum[k] = loss_sum.get(k, 0.0) + v
+                if data_cnt > 0:
+                    break
+        heads = ['p'] + (['v'] if self.stepper.loss_buf.dvalue is not None else []) + \
+            (['r'] if self.stepper.loss_buf.dreturn is not None else []) + ['ent', 'total']
+        print('loss = %s' % ' '.join([k + ':' + '%.3f' % (loss_sum[k] / data_cnt) for k in heads]))
+
+        self.data_cnt_ema = self.data_cnt_ema * 0.8 + data_cnt / (1e-2 + batch_cnt) * 0.2
+        self.lr = self.default_lr * self.data_cnt_ema / (1 + self.steps * 1e-5)
+        self.stepper.opt.set_lr(self.lr)
+        return self._cpu_model()
+
+    def run(self):
+        print('waiting training')
+        while len(self.episodes) < self.args['minimum_episodes']:
+            time.sleep(1)
+        if len(self.params) > 0:
+            self.batcher.run()
+            print('started training')
+        while True:
+            model = self.train()
+            self.update_flag = False
+            self.update_queue.put((model, self.steps))
+
+
+def install():
+    """Swap the reference's learner hot path for this one in an importable `handyrl` package:
+    after `handyrl_b200.train.install()`, `python main.py --train` runs the reference's Learner,
+    workers and server unchanged on top of this Trainer."""
+    import handyrl.train as ref
+    ref.Trainer = Trainer
+    ref.Batcher = Batcher
+    ref.make_batch = make_batch
+    ref.forward_prediction = forward_prediction
+    ref.compute_loss = compute_loss
+    import handyrl.losses as ref_losses
+    ref_losses.compute_target = ops.compute_target
+    return ref

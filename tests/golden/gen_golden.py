@@ -9,6 +9,7 @@ Outputs (committed):
     tests/golden/target_cases.npz   compute_target per algorithm (losses.py:63-80)
     tests/golden/batch_cases.pkl    make_batch on real self-play episodes (train.py:33-124)
     tests/golden/step_cases.pkl     3 full optimiser steps of the reference Trainer maths (train.py:366-371)
+    tests/golden/rnn_cases.pkl      recurrent forward_prediction + compute_loss + parameter gradients (train.py:147-174)
 
 The reference has no golden vectors of its own for this path, so the
 vectors are the reference's own outputs.  The fp64 quirk of `selected_prob` is avoided by
@@ -252,9 +253,51 @@ def gen_step_cases():
     print('step cases:', list(out))
 
 
+def gen_rnn_cases():
+    """Recurrent path: the reference's forward_prediction (train.py:147-174, burn-in, hidden masking)
+    and compute_loss driving a small recurrent net with a dict observation; parameter gradients."""
+    from handyrl_b200.nets import GatedBoardNet
+    out = {}
+    for name, (turn_based, observation, burn_in) in {'alt_burn2': (True, False, 2), 'obs_burn1': (True, True, 1),
+                                                       'sim_burn0': (False, False, 0)}.items():
+        torch.manual_seed(21)
+        net = GatedBoardNet()
+        B, T, P, A = 4, 6, 2, 12
+        args = {'turn_based_training': turn_based, 'observation': observation, 'gamma': 0.8, 'lambda': 0.7,
+                'burn_in_steps': burn_in, 'forward_steps': T - burn_in, 'entropy_regularization': 0.1,
+                'entropy_regularization_decay': 0.1, 'policy_target': 'TD', 'value_target': 'TD'}
+        batch = synthetic_batch(B, T, P, A, turn_based=turn_based, observation=observation, reward_kind='step',
+                                seed=77, burn_in=burn_in, with_obs=False)
+        Pa = batch['action'].shape[2]
+        g = torch.Generator().manual_seed(78)
+        batch['observation'] = {'scalar': torch.rand((B, T, Pa, 4), generator=g),
+                                'board': (torch.rand((B, T, Pa, 3, 4, 4), generator=g) < 0.3).float()}
+        state0 = {k: v.clone().numpy() for k, v in net.state_dict().items()}
+        wrapped = ModelWrapper(net)
+        wrapped.train()
+        hidden = wrapped.init_hidden([B, P])
+        masked = ref_train.forward_prediction(wrapped, hidden, batch, args)
+        masked = {k: v.detach().numpy() for k, v in masked.items()}
+        # fresh copy: forward_prediction updated BatchNorm running stats
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in state0.items()})
+        wrapped.train()
+        losses, dcnt = ref_train.compute_loss(batch, wrapped, wrapped.init_hidden([B, P]), args)
+        losses['total'].backward()
+        from handyrl.util import map_r
+        out[name] = {'args': args, 'dims': (B, T, P, A), 'state0': state0,
+                     'batch': map_r(batch, lambda t: t.numpy()), 'masked_outputs': masked,
+                     'losses': {k: float(v.item()) for k, v in losses.items()}, 'dcnt': float(dcnt),
+                     'param_grads': {k: p.grad.numpy().copy() for k, p in net.named_parameters()},
+                     'state1': {k: v.clone().numpy() for k, v in net.state_dict().items()}}
+    with open(os.path.join(HERE, 'rnn_cases.pkl'), 'wb') as f:
+        pickle.dump(out, f)
+    print('rnn cases:', list(out))
+
+
 if __name__ == '__main__':
     os.chdir('/tmp')
     gen_loss_cases()
     gen_target_cases()
     gen_batch_cases()
     gen_step_cases()
+    gen_rnn_cases()

@@ -67,3 +67,48 @@ def test_clip_adam_oracle_matches_torch():
         norm = oracle.clip_adam(p, g, m, v, 3e-4, step)
         assert abs(norm - ref_norm) <= 1e-5 * ref_norm
         np.testing.assert_allclose(p, tp.detach().numpy(), rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize('name', sorted(LOSS_CASES))
+def test_torch_port_matches_reference(name):
+    """The eager-PyTorch CPU port (bench.py's cpu_baseline / --impl reference) vs the reference."""
+    import torch
+    from oracle import torch_learner
+    case = LOSS_CASES[name]
+    batch, outs, grads, losses = split(case)
+    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+    leaves = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in outs.items()}
+    got, dcnt = torch_learner.loss_from_raw(leaves, tb, case_args(case['meta']))
+    got['total'].backward()
+    assert float(dcnt) == losses['dcnt']
+    for k, ref in losses.items():
+        if k != 'dcnt':
+            assert abs(float(got[k]) - ref) <= RTOL * abs(ref) + 1e-5, (name, k, float(got[k]), ref)
+    for k, ref in grads.items():
+        np.testing.assert_allclose(leaves[k].grad.numpy(), ref, rtol=0, atol=ATOL, err_msg=k)
+
+
+def test_torch_port_full_steps_match_reference():
+    """CpuLearner (model + loss + clip + Adam) reproduces the reference's three optimiser steps."""
+    import os
+    import pickle
+    import torch
+    from conftest import GOLDEN
+    from oracle.torch_learner import CpuLearner
+    from handyrl_b200.nets import tictactoe_net, load_state_by_order
+    from handyrl_b200.synthetic import synthetic_batch
+    with open(os.path.join(GOLDEN, 'step_cases.pkl'), 'rb') as f:
+        cases = pickle.load(f)
+    for name, c in cases.items():
+        B, T, P, A = c['dims']
+        args = c['args']
+        net = load_state_by_order(tictactoe_net(), c['state0'])
+        lrn = CpuLearner(net, args, lr=c['lr'])
+        for s, ref in enumerate(c['steps']):
+            batch = synthetic_batch(B, T, P, A, turn_based=args['turn_based_training'], observation=args['observation'], seed=40 + s)
+            losses, dcnt = lrn.step(batch)
+            assert dcnt == ref['dcnt']
+            for k, v in ref['losses'].items():
+                assert abs(losses[k] - v) <= 1e-5 * abs(v) + 1e-5, (name, s, k)
+        for (k, v), (kr, vr) in zip(net.state_dict().items(), c['state3'].items()):
+            np.testing.assert_allclose(v.numpy(), vr, rtol=1e-5, atol=1e-6, err_msg=k)

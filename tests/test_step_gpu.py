@@ -1,0 +1,95 @@
+"""GPU parity of the WHOLE learner step (net fwd -> fused loss -> net bwd -> clip+Adam) against the
+reference's own three optimiser steps (golden step_cases.pkl) and its recurrent path (rnn_cases.pkl)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+with open(os.path.join(GOLDEN, 'step_cases.pkl'), 'rb') as f:
+    STEP_CASES = pickle.load(f)
+with open(os.path.join(GOLDEN, 'rnn_cases.pkl'), 'rb') as f:
+    RNN_CASES = pickle.load(f)
+
+
+@pytest.fixture(autouse=True)
+def exact_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize('use_graph', [False, True], ids=['eager', 'graph'])
+@pytest.mark.parametrize('name', sorted(STEP_CASES))
+def test_three_learner_steps_match_reference(name, use_graph):
+    from handyrl_b200.nets import tictactoe_net, load_state_by_order
+    from handyrl_b200.synthetic import synthetic_batch
+    from handyrl_b200.train import LearnerStep
+    c = STEP_CASES[name]
+    B, T, P, A = c['dims']
+    args = c['args']
+    net = load_state_by_order(tictactoe_net(), c['state0'])
+    mk = lambda s: synthetic_batch(B, T, P, A, turn_based=args['turn_based_training'], observation=args['observation'], seed=40 + s)
+    stepper = LearnerStep(net, args, mk(0), lr=c['lr'], use_graph=use_graph)
+    for s, ref in enumerate(c['steps']):
+        pk = stepper.new_packed().fill(mk(s))
+        stepper.step(pk)
+        got = stepper.read_losses()
+        for k, v in ref['losses'].items():
+            assert abs(got[k] - v) <= 2e-4 * abs(v) + 1e-4, (s, k, got[k], v)
+        assert got['dcnt'] == ref['dcnt']
+        assert abs(float(stepper.opt.grad_norm) - ref['grad_norm']) <= 1e-3 * ref['grad_norm']
+    final = stepper.cpu_state_dict()
+    for (k, v), (kr, vr) in zip(final.items(), c['state3'].items()):
+        if v.dtype.is_floating_point:
+            np.testing.assert_allclose(v.numpy(), vr, rtol=1e-4, atol=2e-5, err_msg='%s/%s' % (k, kr))
+        else:
+            assert int(v) == int(vr)     # num_batches_tracked
+
+
+@pytest.mark.parametrize('name', sorted(RNN_CASES))
+def test_recurrent_compute_loss_and_param_grads(name):
+    from handyrl_b200.batch import tree_map
+    from handyrl_b200.nets import GatedBoardNet
+    from handyrl_b200.train import compute_loss
+    c = RNN_CASES[name]
+    net = GatedBoardNet()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in c['state0'].items()})
+    net = net.cuda().train()
+    batch = tree_map(lambda a: torch.from_numpy(a).cuda(), c['batch'])
+    B, T, P, A = c['dims']
+    hidden = tree_map(lambda h: h.cuda(), net.init_hidden([B, P]))
+    losses, dcnt = compute_loss(batch, net, hidden, c['args'])
+    losses['total'].backward()
+    assert dcnt == c['dcnt']
+    for k, v in c['losses'].items():
+        assert abs(float(losses[k]) - v) <= 1e-4 * abs(v) + 1e-4, (k, float(losses[k]), v)
+    for k, p in net.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), c['param_grads'][k], rtol=1e-3, atol=2e-5, err_msg=k)
+
+
+def test_trainer_thread_protocol():
+    """Trainer.run() as the Learner drives it (train.py:389-400, 342-345): feed episodes, call update()."""
+    import threading
+    from handyrl_b200.train import Trainer
+    from handyrl_b200.nets import tictactoe_net
+    with open(os.path.join(GOLDEN, 'batch_cases.pkl'), 'rb') as f:
+        case = pickle.load(f)['tictactoe']
+    args = dict(case['args'], batch_size=8, minimum_episodes=4, num_batchers=1, **{'lambda': 0.7},
+                entropy_regularization=0.1, entropy_regularization_decay=0.1, policy_target='UPGO', value_target='VTRACE')
+    tr = Trainer(args, tictactoe_net())
+    tr.episodes.extend(case['episodes'])
+    th = threading.Thread(target=tr.run, daemon=True)
+    th.start()
+    model, steps = tr.update()
+    assert steps >= 1 and not model.training and next(model.parameters()).device.type == 'cpu'
+    model2, steps2 = tr.update()
+    assert steps2 > steps
+    assert any(not torch.equal(a, b) for a, b in zip(model.state_dict().values(), model2.state_dict().values()))
