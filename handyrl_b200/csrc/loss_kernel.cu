@@ -9,420 +9,493 @@
 //   + the autograd pass of train.py:369 through those ops (closed-form gradients
 //     w.r.t. the raw policy / value / return outputs of the net).
 //
-// Mapping (see DESIGN.md "K1"):
-//   CTA        = EPB consecutive episodes (windows) b; all of their T x P x A data stays on chip
-//   phase 0    = small per-cell tensors -> shared memory, coalesced
-//   phase 1    = one group of LPR lanes per policy row (b,t,pa): masked logits z = raw*scale - amask,
-//                row max / sum-exp / entropy / gather with warp shuffles; z is staged in shared memory
-//   phase 2    = one thread per (b,p) column runs every reverse-time recurrence over T in registers
-//                (value + return stream, target + advantage algorithm), emits per-cell terms
-//   phase 3    = row groups again: dL/dpolicy_raw from the staged z (no second HBM read),
-//                dL/dvalue_raw, dL/dreturn_raw, coalesced streaming stores
-//   phase 4    = block partials -> workspace; the last CTA to finish reduces them in a fixed
-//                order in fp64 (deterministic) and writes the 6 scalars.
-#include "common.cuh"
-#include <math.h>
+// CTA = EPB consecutive episodes (windows); all of their T x P x A data stays on chip between the
+// statistics pass and the gradient pass, so every input byte is read from HBM once and every gradient
+// byte written once.  Three data-movement variants share the same maths (loss_common.cuh):
+//
+//   rows kernel, staged I/O   small/medium rows: the episodes' logits and action masks are copied to
+//                             shared memory with cp.async (all in flight at once, one DRAM round trip),
+//                             rows are processed from shared memory, gradients are written back in place
+//                             and leave with one coalesced copy-out.
+//   rows kernel, direct       fallback for shapes that do not fit: coalesced (vector) global loads per row.
+//   bulk kernel               wide rows (A % 4 == 0): TMA 1-D bulk copies (cp.async.bulk + mbarrier) stream
+//                             the logits of the whole episode and a ring of action-mask chunks into shared
+//                             memory while consumer warps reduce rows; gradients leave as bulk stores.
+//
+// Phases: (0) stage  (1) per-row softmax statistics  (2a-2c) targets / recurrences / per-cell terms
+//         (publish six block partials; the last CTA folds them in a fixed order in fp64)
+//         (3) gradients.
+#include "loss_common.cuh"
+#include <stdlib.h>
 
 namespace hrl {
 
-struct LossParams {
-    HrlLossArgs a;
-    int Tt;       // trained steps = T - burn_in
-    int EPB;      // episodes per CTA
-    int stage_z;  // masked logits kept in shared memory between phase 1 and 3
-    int has_v, has_r;
-};
+#define HRL_STAMP(i)                                                                             \
+    do {                                                                                         \
+        if (prm.trace && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) prm.trace[i] = clock64(); \
+    } while (0)
 
-// shared-memory carve-up, in floats
-struct SmemLayout {
-    int emask, prog;                               // [cells]
-    int tm, om, rew, ret, wterm, dv, dr;           // [cols]
-    int outcome;                                   // [EPB*P]
-    int logp, rho, ent, mx, lsum, scale, vraw, rraw, act;  // [rows]
-    int red;                                       // [8*32]
-    int z;                                         // [rows*A] if staged
-    int total;
-};
-
-__host__ __device__ inline SmemLayout make_layout(int EPB, int Tt, int P, int Pa, int A, int stage_z) {
-    SmemLayout L;
-    int cells = EPB * Tt, cols = cells * P, rows = cells * Pa, o = 0;
-    L.emask = o; o += cells;
-    L.prog = o; o += cells;
-    L.tm = o; o += cols;
-    L.om = o; o += cols;
-    L.rew = o; o += cols;
-    L.ret = o; o += cols;
-    L.wterm = o; o += cols;
-    L.dv = o; o += cols;
-    L.dr = o; o += cols;
-    L.outcome = o; o += EPB * P;
-    L.logp = o; o += rows;
-    L.rho = o; o += rows;
-    L.ent = o; o += rows;
-    L.mx = o; o += rows;
-    L.lsum = o; o += rows;
-    L.scale = o; o += rows;
-    L.vraw = o; o += rows;
-    L.rraw = o; o += rows;
-    L.act = o; o += rows;
-    o = (o + 3) & ~3;
-    L.red = o; o += 8 * 32;
-    L.z = o;
-    if (stage_z) o += rows * A;
-    L.total = o;
-    return L;
+// element index of the k-th value a lane holds: the scalar layout interleaves lanes; the vector layout
+// (LPR == 32, A % 4 == 0) gives every lane float4 chunks so that a warp touches 512 contiguous bytes.
+template <int LPR, bool VEC>
+__device__ __forceinline__ int elem_index(int k, int lane) {
+    return VEC ? ((k >> 2) * LPR + lane) * 4 + (k & 3) : k * LPR + lane;
 }
 
-// One reverse-time step of one recurrence (losses.py:16-60).  `st*` carry the values of step t+1.
-struct Chain {
-    float G;        // TD / UPGO target at t+1
-    float acc;      // V-Trace vs - v at t+1
-    float vs_next;  // V-Trace vs at t+1
-};
+__device__ __forceinline__ CtaCtx make_ctx(const LossParams &prm) {
+    CtaCtx c;
+    const HrlLossArgs &a = prm.a;
+    c.T0 = a.T; c.P = a.P; c.Pa = a.Pa; c.A = a.A; c.bi = a.burn_in; c.Tt = prm.Tt;
+    c.b0 = blockIdx.x * prm.EPB;
+    c.nE = min(prm.EPB, a.B - c.b0);
+    c.tid = threadIdx.x; c.nthr = blockDim.x;
+    c.nrows = c.nE * c.Tt * c.Pa; c.ncols = c.nE * c.Tt * c.P; c.ncells = c.nE * c.Tt;
+    return c;
+}
 
-__device__ __forceinline__ void chain_step(int algo, bool has_baseline, bool last, float v_t, float v_next,
-                                           float lam_next, float r_t, float gamma, float boot, float ret_t,
-                                           float rho_t, float c_t, Chain &s, float &tgt, float &adv) {
-    if (!has_baseline) {  // losses.py:64-66
-        tgt = ret_t;
-        adv = ret_t;
-        return;
+// phase 0: every small per-cell tensor of the CTA's episodes -> shared memory, asynchronously
+__device__ __forceinline__ void stage_small(const LossParams &prm, const SmemLayout &L, float *smem, const CtaCtx &c) {
+    const HrlLossArgs &a = prm.a;
+    const int R = c.Tt * c.Pa;
+    for (int i = c.tid; i < c.ncols; i += c.nthr) {
+        const int e = i / (c.Tt * c.P), r = i - e * (c.Tt * c.P);
+        const size_t g = ((size_t)(c.b0 + e) * c.T0 + c.bi) * c.P + r;
+        cp_async4(smem + L.tm + i, a.turn_mask + g);
+        cp_async4(smem + L.om + i, a.observation_mask + g);
+        cp_async4(smem + L.rew + i, a.reward + g);
+        cp_async4(smem + L.ret + i, a.ret + g);
     }
-    switch (algo) {
-        case HRL_MC:  // losses.py:16-17
-            tgt = ret_t;
-            adv = ret_t - v_t;
-            break;
-        case HRL_TD:  // losses.py:20-29
-            s.G = last ? boot : r_t + gamma * ((1.0f - lam_next) * v_next + lam_next * s.G);
-            tgt = s.G;
-            adv = s.G - v_t;
-            break;
-        case HRL_UPGO:  // losses.py:32-42
-            s.G = last ? boot : r_t + gamma * fmaxf(v_next, (1.0f - lam_next) * v_next + lam_next * s.G);
-            tgt = s.G;
-            adv = s.G - v_t;
-            break;
-        default: {  // HRL_VTRACE, losses.py:45-60
-            float vn = last ? boot : v_next;
-            float delta = rho_t * (r_t + gamma * vn - v_t);
-            s.acc = last ? delta : delta + gamma * lam_next * c_t * s.acc;
-            float vs = s.acc + v_t;
-            adv = r_t + gamma * (last ? boot : s.vs_next) - v_t;
-            s.vs_next = vs;
-            tgt = vs;
+    for (int i = c.tid; i < c.ncells; i += c.nthr) {
+        const int e = i / c.Tt, r = i - e * c.Tt;
+        const size_t g = (size_t)(c.b0 + e) * c.T0 + c.bi + r;
+        cp_async4(smem + L.emask + i, a.episode_mask + g);
+        cp_async4(smem + L.prog + i, a.progress + g);
+    }
+    long long *s_act = reinterpret_cast<long long *>(smem + L.act);
+    for (int i = c.tid; i < c.nrows; i += c.nthr) {
+        const int e = i / R, r = i - e * R;
+        const size_t g = ((size_t)(c.b0 + e) * c.T0 + c.bi) * c.Pa + r;
+        if (prm.has_v) cp_async4(smem + L.vraw + i, a.value_raw + g); else smem[L.vraw + i] = 0.0f;
+        if (prm.has_r) cp_async4(smem + L.rraw + i, a.return_raw + g); else smem[L.rraw + i] = 0.0f;
+        cp_async4(smem + L.prob + i, a.selected_prob + g);
+        cp_async8(s_act + i, a.action + g);
+    }
+    for (int i = c.tid; i < c.nE * c.P; i += c.nthr) cp_async4(smem + L.outcome + i, a.outcome + (size_t)c.b0 * c.P + i);
+}
+
+// burn-in steps take no part in the loss: zero gradients (train.py:220-222)
+__device__ __forceinline__ void zero_burn_in(const LossParams &prm, const CtaCtx &c) {
+    const HrlLossArgs &a = prm.a;
+    if (c.bi <= 0) return;
+    const int nz = c.bi * c.Pa * c.A, nzr = c.bi * c.Pa;
+    for (int e = 0; e < c.nE; e++) {
+        const size_t g0 = (size_t)(c.b0 + e) * c.T0 * c.Pa;
+        for (int i = c.tid; i < nz; i += c.nthr) a.dpolicy_raw[g0 * c.A + i] = 0.0f;
+        for (int i = c.tid; i < nzr; i += c.nthr) {
+            if (prm.has_v) a.dvalue_raw[g0 + i] = 0.0f;
+            if (prm.has_r) a.dreturn_raw[g0 + i] = 0.0f;
         }
     }
 }
 
-template <int LPR, int NPL>
-__global__ void __launch_bounds__(512) loss_fwd_bwd_kernel(const LossParams prm) {
-    extern __shared__ __align__(16) float smem[];
+// per-row tail of the statistics pass: gather, importance ratio, taps
+__device__ __forceinline__ void finish_row(const LossParams &prm, const SmemLayout &L, float *smem, int r, size_t grow,
+                                           float za, float m, float lsum, float h, float em, float mu, float scale) {
     const HrlLossArgs &a = prm.a;
-    const int T0 = a.T, P = a.P, Pa = a.Pa, A = a.A, bi = a.burn_in, Tt = prm.Tt;
-    const int b0 = blockIdx.x * prm.EPB;
-    const int nE = min(prm.EPB, a.B - b0);
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const SmemLayout L = make_layout(prm.EPB, Tt, P, Pa, A, prm.stage_z);
-    const int R = Tt * Pa;           // rows per episode
-    const int nrows = nE * R, ncols = nE * Tt * P, ncells = nE * Tt;
-    int *s_act = reinterpret_cast<int *>(smem + L.act);
+    const float lt = (za - m - lsum) * em;                              // train.py:232
+    const float lb = logf(fminf(fmaxf(mu, 1e-16f), 1.0f)) * em;         // train.py:231
+    const float rho = fminf(fmaxf(expf(lt - lb), 0.0f), 1.0f);          // train.py:235-238
+    smem[L.logp + r] = lt;
+    smem[L.rho + r] = rho;
+    smem[L.ent + r] = h;
+    smem[L.mx + r] = m;
+    smem[L.lsum + r] = lsum;
+    smem[L.scale + r] = scale;
+    if (a.tap_logp) a.tap_logp[grow] = lt;
+    if (a.tap_rho) a.tap_rho[grow] = rho;
+    if (a.tap_entropy) a.tap_entropy[grow] = h;
+}
 
-    // ---------------- phase 0: small tensors -> smem (coalesced; each episode's slice is contiguous)
-    for (int i = tid; i < ncols; i += nthr) {
-        int e = i / (Tt * P), r = i - e * (Tt * P);
-        size_t g = ((size_t)(b0 + e) * T0 + bi) * P + r;
-        smem[L.tm + i] = a.turn_mask[g];
-        smem[L.om + i] = a.observation_mask[g];
-        smem[L.rew + i] = a.reward[g];
-        smem[L.ret + i] = a.ret[g];
+// ======================================================================== rows kernel
+// IOS: logits and action masks staged in shared memory by cp.async (rows read/written on chip only).
+template <int LPR, int NPL, bool VEC, bool IOS>
+__global__ void __launch_bounds__(512) loss_rows_kernel(const LossParams prm) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ bool s_last;
+    const HrlLossArgs &a = prm.a;
+    const CtaCtx c = make_ctx(prm);
+    const int P = c.P, Pa = c.Pa, A = c.A, Tt = c.Tt, T0 = c.T0, bi = c.bi, tid = c.tid, nthr = c.nthr;
+    const int R = Tt * Pa, RS = prm.row_stride;
+    const SmemLayout L = make_layout(prm.EPB, Tt, P, Pa, prm.stage_z, RS, IOS ? prm.EPB * R * RS : 0);
+    const long long *s_act = reinterpret_cast<const long long *>(smem + L.act);
+    HRL_STAMP(0);
+
+    // ---------------- phase 0: stage
+    stage_small(prm, L, smem, c);
+    if (IOS) {
+        const int per_ep = R * A;
+        for (int i = tid; i < c.nE * per_ep; i += nthr) {
+            const int e = i / per_ep, rem = i - e * per_ep;
+            const int rr = rem / A, j = rem - rr * A;
+            const size_t g = ((size_t)(c.b0 + e) * T0 + bi) * Pa * A + rem;
+            const int s = (e * R + rr) * RS + j;
+            cp_async4(smem + L.z + s, a.policy_raw + g);
+            cp_async4(smem + L.am + s, a.action_mask + g);
+        }
+        cp_async_wait_all();
+        __syncthreads();
     }
-    for (int i = tid; i < ncells; i += nthr) {
-        int e = i / Tt, r = i - e * Tt;
-        size_t g = (size_t)(b0 + e) * T0 + bi + r;
-        smem[L.emask + i] = a.episode_mask[g];
-        smem[L.prog + i] = a.progress[g];
-    }
-    for (int i = tid; i < nrows; i += nthr) {
-        int e = i / R, r = i - e * R;
-        size_t g = ((size_t)(b0 + e) * T0 + bi) * Pa + r;
-        smem[L.vraw + i] = prm.has_v ? a.value_raw[g] : 0.0f;
-        smem[L.rraw + i] = prm.has_r ? a.return_raw[g] : 0.0f;
-        s_act[i] = (int)a.action[g];
-    }
-    for (int i = tid; i < nE * P; i += nthr) smem[L.outcome + i] = a.outcome[(size_t)b0 * P + i];
+    HRL_STAMP(1);
 
     // ---------------- phase 1: per-row softmax statistics
     const int grp = tid / LPR, lane = tid % LPR, ngrp = nthr / LPR;
-    for (int base = 0; base < nrows; base += ngrp) {
+    for (int base = 0; base < c.nrows; base += ngrp) {
         const int r = base + grp;
-        const bool valid = r < nrows;
+        const bool valid = r < c.nrows;
         float z[NPL];
         float scale = 0.0f, em = 0.0f, mu = 1.0f;
         int act = 0;
         size_t grow = 0;
         if (valid) {
-            int e = r / R, rr = r - e * R, t = rr / Pa, q = rr - t * Pa;
-            size_t cell = (size_t)(b0 + e) * T0 + bi + t;
+            const int e = r / R, rr = r - e * R, t = rr / Pa, q = rr - t * Pa;
+            const size_t cell = (size_t)(c.b0 + e) * T0 + bi + t;
             grow = cell * Pa + q;
-            if (Pa == P) {
-                scale = a.turn_mask[cell * P + q];
-            } else {  // turn-alternating batch: sum over players (train.py:179-180)
-                for (int p = 0; p < P; p++) scale += a.turn_mask[cell * P + p];
+            if (IOS) {
+                const int scell = e * Tt + t;
+                if (Pa == P) scale = smem[L.tm + scell * P + q];
+                else for (int p = 0; p < P; p++) scale += smem[L.tm + scell * P + p];   // train.py:179-180
+                em = smem[L.emask + scell];
+                mu = smem[L.prob + r];
+                act = (int)s_act[r];
+            } else {
+                if (Pa == P) scale = a.turn_mask[cell * P + q];
+                else for (int p = 0; p < P; p++) scale += a.turn_mask[cell * P + p];
+                em = a.episode_mask[cell];
+                mu = a.selected_prob[grow];
+                act = (int)a.action[grow];
             }
-            em = a.episode_mask[cell];
-            mu = a.selected_prob[grow];
-            act = (int)a.action[grow];
         }
         const float *rawp = a.policy_raw + grow * A;
         const float *amp = a.action_mask + grow * A;
         float m = -INFINITY, za = -INFINITY;
+        if (VEC) {
+#pragma unroll
+            for (int k4 = 0; k4 < NPL / 4; k4++) {
+                const int j = (k4 * LPR + lane) * 4;
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f), am = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+                if (valid && j < A) {
+                    x = __ldcs(reinterpret_cast<const float4 *>(rawp + j));
+                    am = __ldcs(reinterpret_cast<const float4 *>(amp + j));
+                }
+                z[k4 * 4 + 0] = x.x * scale - am.x;  // train.py:178-181
+                z[k4 * 4 + 1] = x.y * scale - am.y;
+                z[k4 * 4 + 2] = x.z * scale - am.z;
+                z[k4 * 4 + 3] = x.w * scale - am.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NPL; k++) {
+                const int j = k * LPR + lane;
+                z[k] = -INFINITY;
+                if (valid && j < A) {
+                    if (IOS) z[k] = smem[L.z + r * RS + j] * scale - smem[L.am + r * RS + j];
+                    else z[k] = ld_stream(rawp + j) * scale - ld_stream(amp + j);
+                }
+            }
+        }
 #pragma unroll
         for (int k = 0; k < NPL; k++) {
-            int j = k * LPR + lane;
-            z[k] = -INFINITY;
-            if (valid && j < A) {
-                z[k] = ld_stream(rawp + j) * scale - ld_stream(amp + j);  // train.py:178-181
-                if (j == act) za = z[k];
-            }
+            if (elem_index<LPR, VEC>(k, lane) == act) za = z[k];
             m = fmaxf(m, z[k]);
         }
         m = group_max<LPR>(m);
         za = group_max<LPR>(za);
-        float se = 0.0f;
+        // one exp per element: S = sum e, W = sum e * (z - m);  entropy = log S - W / S
+        float se = 0.0f, sw = 0.0f;
 #pragma unroll
         for (int k = 0; k < NPL; k++) {
-            int j = k * LPR + lane;
-            if (j < A) se += expf(z[k] - m);
+            const int j = elem_index<LPR, VEC>(k, lane);
+            if (valid && j < A) {
+                const float d = z[k] - m;
+                const float ex = expf(d);
+                se += ex;
+                sw += ex * fmaxf(d, -3.0e38f);     // e = 0 rows contribute 0, never 0 * inf
+                if (prm.stage_z) smem[L.z + r * RS + j] = z[k];
+            }
         }
         se = group_sum<LPR>(se);
-        const float lsum = logf(se);
-        float h = 0.0f;
-#pragma unroll
-        for (int k = 0; k < NPL; k++) {
-            int j = k * LPR + lane;
-            if (valid && j < A) {
-                float lp = z[k] - m - lsum;
-                float pj = expf(lp);
-                h -= pj * fmaxf(lp, -3.402823466e38f);  // Categorical.entropy clamps logits at finfo.min
-                if (prm.stage_z) smem[L.z + (size_t)r * A + j] = z[k];
-            }
-        }
-        h = group_sum<LPR>(h);
+        sw = group_sum<LPR>(sw);
         if (valid && lane == 0) {
-            float lt = (za - m - lsum) * em;                              // train.py:232
-            float lb = logf(fminf(fmaxf(mu, 1e-16f), 1.0f)) * em;         // train.py:231
-            float rho = fminf(fmaxf(expf(lt - lb), 0.0f), 1.0f);          // train.py:235-238
-            smem[L.logp + r] = lt;
-            smem[L.rho + r] = rho;
-            smem[L.ent + r] = h;
-            smem[L.mx + r] = m;
-            smem[L.lsum + r] = lsum;
-            smem[L.scale + r] = scale;
-            if (a.tap_logp) a.tap_logp[grow] = lt;
-            if (a.tap_rho) a.tap_rho[grow] = rho;
-            if (a.tap_entropy) a.tap_entropy[grow] = h;
+            const float lsum = logf(se);
+            finish_row(prm, L, smem, r, grow, za, m, lsum, lsum - sw / se, em, mu, scale);
         }
     }
+    if (!IOS) cp_async_wait_all();
+    HRL_STAMP(2);
     __syncthreads();
+    HRL_STAMP(3);
 
-    // ---------------- phase 2: reverse-time recurrences, one thread per (episode, player) column
-    float Lp = 0.f, Lv = 0.f, Lr = 0.f, Lent = 0.f, Lreg = 0.f, dcnt = 0.f;
-    if (tid < nE * P) {
-        const int e = tid / P, p = tid - e * P;
-        const int q = (Pa == P) ? p : 0;
-        const bool sym = a.two_player_zero_sum && P == 2;
-        const int po = sym ? 1 - p : p, qo = (Pa == P) ? po : 0;
-        const float lmb = a.lambda, gam = a.gamma, dec = a.entropy_regularization_decay;
-        const float oc = smem[L.outcome + e * P + p];
-        const int vt = a.value_target, pt = a.policy_target;
-        const bool two = (pt != vt);
-        const size_t gcol0 = ((size_t)(b0 + e) * T0 + bi) * P + p;
-        const float boot_r = smem[L.ret + (e * Tt + Tt - 1) * P + p];  // returns[:, -1]
-        Chain cv = {0, 0, 0}, cv2 = {0, 0, 0}, cr = {0, 0, 0}, cr2 = {0, 0, 0};
-        float v_next = 0.f, lamv_next = 0.f, r_next = 0.f, lamr_next = 0.f;
-        for (int t = Tt - 1; t >= 0; t--) {
-            const int cell = e * Tt + t, col = cell * P + p, row = cell * Pa + q;
-            const float om = smem[L.om + col], tm = smem[L.tm + col], em = smem[L.emask + cell];
-            const float vout = smem[L.vraw + row] * om;      // train.py:184
-            const float rout = smem[L.rraw + row] * om;
-            float vb = vout, vm = om;
-            if (sym) {  // train.py:243-247
-                const float omo = smem[L.om + cell * P + po];
-                const float vo = -(smem[L.vraw + cell * Pa + qo] * omo);
-                vb = (vout * om + vo * omo) / (om + omo + 1e-8f);
-                vm = fminf(fmaxf(om + omo, 0.0f), 1.0f);
-            }
-            vb = vb * em + oc * (1.0f - em);                 // train.py:248
-            const float lamv = lmb + (1.0f - lmb) * (1.0f - vm);   // losses.py:71
-            const float lamr = lmb + (1.0f - lmb) * (1.0f - om);
-            const float rho = smem[L.rho + row];
-            const float rew = smem[L.rew + col], ret = smem[L.ret + col];
-            const bool last = (t == Tt - 1);
-            float tgv, adv_v, tgr, adv_r, dummy;
-            chain_step(vt, prm.has_v, last, vb, v_next, lamv_next, 0.0f, 1.0f, oc, oc, rho, rho, cv, tgv, adv_v);
-            chain_step(vt, prm.has_r, last, rout, r_next, lamr_next, rew, gam, boot_r, ret, rho, rho, cr, tgr, adv_r);
-            if (two) {  // train.py:260-262
-                chain_step(pt, prm.has_v, last, vb, v_next, lamv_next, 0.0f, 1.0f, oc, oc, rho, rho, cv2, dummy, adv_v);
-                chain_step(pt, prm.has_r, last, rout, r_next, lamr_next, rew, gam, boot_r, ret, rho, rho, cr2, dummy, adv_r);
-            }
-            v_next = vb; lamv_next = lamv; r_next = rout; lamr_next = lamr;
-
-            const float tot_adv = rho * (adv_v + adv_r);     // train.py:265
-            smem[L.wterm + col] = tot_adv * tm;
-            Lp += -smem[L.logp + row] * tot_adv * tm;        // train.py:202
-            float dv = 0.f, dr = 0.f;
-            if (prm.has_v) {                                  // train.py:204
-                float d = vout - tgv;
-                Lv += d * d * om;
-                dv = d * om * om;
-            }
-            if (prm.has_r) {                                  // train.py:206 smooth_l1, beta 1
-                float d = rout - tgr, ad = fabsf(d);
-                Lr += (ad < 1.0f ? 0.5f * d * d : ad - 0.5f) * om;
-                dr = fminf(fmaxf(d, -1.0f), 1.0f) * om * om;
-            }
-            smem[L.dv + col] = dv;
-            smem[L.dr + col] = dr;
-            const float h = smem[L.ent + row] * tm;          // train.py:208
-            Lent += h;
-            Lreg += h * (1.0f - smem[L.prog + cell] * (1.0f - dec));   // train.py:212
-            dcnt += tm;
-            const size_t gcol = gcol0 + (size_t)t * P;
-            if (a.tap_target_value) a.tap_target_value[gcol] = tgv;
-            if (a.tap_target_return) a.tap_target_return[gcol] = tgr;
-            if (a.tap_advantage) a.tap_advantage[gcol] = tot_adv;
-        }
-    }
-    __syncthreads();
+    // ---------------- phase 2: targets, recurrences, per-cell terms; publish the scalars
+    float part[6];
+    targets_and_losses(prm, L, smem, c, part);
+    HRL_STAMP(4);
+    const bool last = publish_partials(prm, L, smem, c, part, &s_last);
+    if (last) finalize_losses(prm, L, smem, c);
+    HRL_STAMP(5);
 
     // ---------------- phase 3: gradients w.r.t. the raw net outputs
-    const float creg = a.entropy_regularization;
-    for (int base = 0; base < nrows; base += ngrp) {
+    for (int base = 0; base < c.nrows; base += ngrp) {
         const int r = base + grp;
-        if (r >= nrows) continue;  // no shuffles below: divergence is harmless
+        if (r >= c.nrows) continue;  // no shuffles below: divergence is harmless
         const int e = r / R, rr = r - e * R, t = rr / Pa, q = rr - t * Pa;
         const int cell = e * Tt + t;
-        const size_t grow = ((size_t)(b0 + e) * T0 + bi + t) * Pa + q;
-        float w = 0.f, k = 0.f, gv = 0.f, gr = 0.f;
-        if (Pa == P) {
-            w = smem[L.wterm + cell * P + q];
-            k = smem[L.tm + cell * P + q];
-            gv = smem[L.dv + cell * P + q];
-            gr = smem[L.dr + cell * P + q];
-        } else {
-            for (int p = 0; p < P; p++) {
-                w += smem[L.wterm + cell * P + p];
-                k += smem[L.tm + cell * P + p];
-                gv += smem[L.dv + cell * P + p];
-                gr += smem[L.dr + cell * P + p];
-            }
-        }
-        w *= smem[L.emask + cell];
-        k *= creg * (1.0f - smem[L.prog + cell] * (1.0f - a.entropy_regularization_decay));
+        const size_t grow = ((size_t)(c.b0 + e) * T0 + bi + t) * Pa + q;
+        const RowFactors f = row_factors(prm, L, smem, cell, q, P, Pa);
         const float scale = smem[L.scale + r], m = smem[L.mx + r], lsum = smem[L.lsum + r], h = smem[L.ent + r];
-        const int act = s_act[r];
+        const int act = (int)s_act[r];
         float *outp = a.dpolicy_raw + grow * A;
-        if (scale == 0.0f) {
+        const float *rawp = a.policy_raw + grow * A;
+        const float *amp = a.action_mask + grow * A;
+        if (VEC) {
 #pragma unroll
-            for (int kk = 0; kk < NPL; kk++) {
-                int j = kk * LPR + lane;
-                if (j < A) st_stream(outp + j, 0.0f);
+            for (int k4 = 0; k4 < NPL / 4; k4++) {
+                const int j = (k4 * LPR + lane) * 4;
+                if (j < A) {
+                    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (scale != 0.0f) {
+                        float zz[4];
+                        if (prm.stage_z) {
+                            const float4 t4 = *reinterpret_cast<const float4 *>(smem + L.z + r * RS + j);
+                            zz[0] = t4.x; zz[1] = t4.y; zz[2] = t4.z; zz[3] = t4.w;
+                        } else {
+                            const float4 x = *reinterpret_cast<const float4 *>(rawp + j);
+                            const float4 am = *reinterpret_cast<const float4 *>(amp + j);
+                            zz[0] = x.x * scale - am.x; zz[1] = x.y * scale - am.y;
+                            zz[2] = x.z * scale - am.z; zz[3] = x.w * scale - am.w;
+                        }
+                        out.x = grad_elem(zz[0], j + 0 == act, m, lsum, h, f.w, f.k, scale);
+                        out.y = grad_elem(zz[1], j + 1 == act, m, lsum, h, f.w, f.k, scale);
+                        out.z = grad_elem(zz[2], j + 2 == act, m, lsum, h, f.w, f.k, scale);
+                        out.w = grad_elem(zz[3], j + 3 == act, m, lsum, h, f.w, f.k, scale);
+                    }
+                    __stcs(reinterpret_cast<float4 *>(outp + j), out);
+                }
             }
         } else {
-            const float *rawp = a.policy_raw + grow * A;
-            const float *amp = a.action_mask + grow * A;
 #pragma unroll
             for (int kk = 0; kk < NPL; kk++) {
-                int j = kk * LPR + lane;
+                const int j = kk * LPR + lane;
                 if (j < A) {
-                    float zj = prm.stage_z ? smem[L.z + (size_t)r * A + j] : (rawp[j] * scale - amp[j]);
-                    float lp = zj - m - lsum;
-                    float pj = expf(lp);
-                    float dz = -w * ((j == act ? 1.0f : 0.0f) - pj);
-                    if (pj > 0.0f) dz += k * pj * (lp + h);
-                    st_stream(outp + j, dz * scale);
+                    float g = 0.0f;
+                    if (scale != 0.0f) {
+                        const float zj = prm.stage_z ? smem[L.z + r * RS + j] : (rawp[j] * scale - amp[j]);
+                        g = grad_elem(zj, j == act, m, lsum, h, f.w, f.k, scale);
+                    }
+                    if (IOS) smem[L.z + r * RS + j] = g;      // leaves with the coalesced copy-out below
+                    else st_stream(outp + j, g);
                 }
             }
         }
         if (lane == 0) {
-            if (prm.has_v) a.dvalue_raw[grow] = gv;
-            if (prm.has_r) a.dreturn_raw[grow] = gr;
+            if (prm.has_v) a.dvalue_raw[grow] = f.gv;
+            if (prm.has_r) a.dreturn_raw[grow] = f.gr;
         }
     }
-    // burn-in steps take no part in the loss: zero gradients (train.py:220-222)
-    if (bi > 0) {
-        const int nz = bi * Pa * A, nzr = bi * Pa;
-        for (int e = 0; e < nE; e++) {
-            size_t g0 = (size_t)(b0 + e) * T0 * Pa;
-            for (int i = tid; i < nz; i += nthr) a.dpolicy_raw[g0 * A + i] = 0.0f;
-            for (int i = tid; i < nzr; i += nthr) {
-                if (prm.has_v) a.dvalue_raw[g0 + i] = 0.0f;
-                if (prm.has_r) a.dreturn_raw[g0 + i] = 0.0f;
-            }
-        }
-    }
-
-    // ---------------- phase 4: deterministic reduction of the six scalars
-    float part[6] = {Lp, Lv, Lr, Lent, Lreg, dcnt};
-    const int warp = tid >> 5, wl = tid & 31, nwarp = (nthr + 31) >> 5;
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-        float v = warp_sum(part[i]);
-        if (wl == 0) smem[L.red + i * 32 + warp] = v;
-    }
-    __syncthreads();
-    unsigned int *counter = reinterpret_cast<unsigned int *>(a.workspace);
-    float *partials = reinterpret_cast<float *>(reinterpret_cast<char *>(a.workspace) + 256);
-    __shared__ bool is_last;
-    if (tid == 0) {
-        for (int i = 0; i < 6; i++) {
-            float v = 0.f;
-            for (int w2 = 0; w2 < nwarp; w2++) v += smem[L.red + i * 32 + w2];
-            partials[(size_t)blockIdx.x * 8 + i] = v;
-        }
-        __threadfence();
-        unsigned int ticket = atomicAdd(counter, 1u);
-        is_last = (ticket == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        double acc[6] = {0, 0, 0, 0, 0, 0};
-        for (int blk = tid; blk < (int)gridDim.x; blk += nthr) {
-#pragma unroll
-            for (int i = 0; i < 6; i++) acc[i] += (double)__ldcg(partials + (size_t)blk * 8 + i);
-        }
-        double *dred = reinterpret_cast<double *>(smem + L.red);  // 8*32 floats = 128 doubles >= 6*16
+    if (IOS) {
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            double v = warp_sum_d(acc[i]);
-            if (wl == 0) dred[i * 16 + warp] = v;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double s[6];
-            for (int i = 0; i < 6; i++) {
-                s[i] = 0;
-                for (int w2 = 0; w2 < nwarp; w2++) s[i] += dred[i * 16 + w2];
-            }
-            double lv = 0.5 * s[1];
-            a.losses[HRL_LOSS_P] = (float)s[0];
-            a.losses[HRL_LOSS_V] = (float)lv;
-            a.losses[HRL_LOSS_R] = (float)s[2];
-            a.losses[HRL_LOSS_ENT] = (float)s[3];
-            a.losses[HRL_LOSS_TOTAL] = (float)(s[0] + lv + s[2] - (double)creg * s[4]);  // train.py:211-213
-            a.losses[HRL_LOSS_DCNT] = (float)s[5];
-            *counter = 0u;  // leave the workspace ready for the next launch
+        const int per_ep = R * A;
+        for (int i = tid; i < c.nE * per_ep; i += nthr) {
+            const int e = i / per_ep, rem = i - e * per_ep;
+            const int rr = rem / A, j = rem - rr * A;
+            st_stream(a.dpolicy_raw + ((size_t)(c.b0 + e) * T0 + bi) * Pa * A + rem, smem[L.z + (e * R + rr) * RS + j]);
         }
     }
+    zero_burn_in(prm, c);
+    HRL_STAMP(6);
 }
 
-template <int LPR, int NPL>
-static int launch(const LossParams &prm, int grid, int threads, size_t smem_bytes, cudaStream_t stream) {
-    auto kern = loss_fwd_bwd_kernel<LPR, NPL>;
+// ======================================================================== bulk (TMA) kernel
+// One episode per CTA, A % 4 == 0.  Warps 0..NC-1 consume rows, warp NC produces: it issues
+//   * one bulk load per chunk of `chunk_rows` logit rows into zbuf (the whole episode is in flight at once),
+//   * bulk loads of the matching action-mask chunks into an `n_stage`-deep ring, refilled as consumers release slots.
+// A consumer warp owns row (chunk * chunk_rows + warp): 32 lanes x float4 from shared memory, statistics with
+// shuffles, masked logits written back in place.  After the recurrences the same warp turns its rows into
+// gradients in place and sends each row home with a bulk store.
+__global__ void __launch_bounds__(576, 1) loss_bulk_kernel(const LossParams prm) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ bool s_last;
+    const HrlLossArgs &a = prm.a;
+    const CtaCtx c = make_ctx(prm);
+    const int P = c.P, Pa = c.Pa, A = c.A, Tt = c.Tt, T0 = c.T0, bi = c.bi, tid = c.tid;
+    const int R = Tt * Pa, G = prm.chunk_rows, NS = prm.n_stage;
+    const int nchunk = (R + G - 1) / G;
+    const SmemLayout L = make_layout(1, Tt, P, Pa, 1, A, NS * G * A);
+    uint64_t *raw_full = reinterpret_cast<uint64_t *>(smem + L.bars);
+    uint64_t *am_full = raw_full + kMaxChunks, *am_empty = am_full + kMaxStages;
+    const long long *s_act = reinterpret_cast<const long long *>(smem + L.act);
+    const int warp = tid >> 5, lane = tid & 31;
+    const int NC = (c.nthr >> 5) - 1;   // consumer warps (== chunk_rows)
+    const size_t ep_off = ((size_t)c.b0 * T0 + bi) * Pa * A;   // first trained logit of this episode
+    HRL_STAMP(0);
+
+    if (tid == 0) {
+        for (int i = 0; i < nchunk; i++) mbar_init(raw_full + i, 1);
+        for (int i = 0; i < NS; i++) { mbar_init(am_full + i, 1); mbar_init(am_empty + i, NC); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    stage_small(prm, L, smem, c);
+
+    if (warp == NC) {
+        // ---------------- producer
+        if (lane == 0) {
+            for (int ch = 0; ch < nchunk; ch++) {
+                const int rows = min(G, R - ch * G);
+                const uint32_t bytes = (uint32_t)rows * A * 4;
+                mbar_expect_tx(raw_full + ch, bytes);
+                bulk_load(smem + L.z + (size_t)ch * G * A, a.policy_raw + ep_off + (size_t)ch * G * A, bytes, raw_full + ch);
+            }
+            for (int ch = 0; ch < nchunk; ch++) {
+                const int st = ch % NS;
+                if (ch >= NS) mbar_wait(am_empty + st, ((ch / NS) - 1) & 1);
+                const int rows = min(G, R - ch * G);
+                const uint32_t bytes = (uint32_t)rows * A * 4;
+                mbar_expect_tx(am_full + st, bytes);
+                bulk_load(smem + L.am + (size_t)st * G * A, a.action_mask + ep_off + (size_t)ch * G * A, bytes, am_full + st);
+            }
+        }
+    } else {
+        // ---------------- consumers: statistics pass.  The per-row scalars are read straight from global
+        // memory here (the staged copies only become visible CTA-wide after the barrier below).
+        for (int ch = 0; ch < nchunk; ch++) {
+            const int st = ch % NS;
+            const int rr = ch * G + warp;
+            const bool valid = rr < R;
+            float scale = 0.0f, em = 0.0f, mu = 1.0f;
+            int act = 0;
+            size_t grow = 0;
+            if (valid) {
+                const int t = rr / Pa, q = rr - t * Pa;
+                const size_t cell = (size_t)c.b0 * T0 + bi + t;
+                grow = cell * Pa + q;
+                if (Pa == P) scale = a.turn_mask[cell * P + q];
+                else for (int p = 0; p < P; p++) scale += a.turn_mask[cell * P + p];
+                em = a.episode_mask[cell];
+                mu = a.selected_prob[grow];
+                act = (int)a.action[grow];
+            }
+            mbar_wait(raw_full + ch, 0);
+            mbar_wait(am_full + st, (ch / NS) & 1);
+            if (valid) {
+                float *zrow = smem + L.z + (size_t)rr * A;
+                const float *arow = smem + L.am + ((size_t)st * G + warp) * A;
+                float4 z4[4];
+                float m = -INFINITY;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; k4++) {
+                    const int j = (k4 * 32 + lane) * 4;
+                    z4[k4] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                    if (j < A) {
+                        const float4 x = *reinterpret_cast<const float4 *>(zrow + j);
+                        const float4 am = *reinterpret_cast<const float4 *>(arow + j);
+                        z4[k4].x = fmaf(x.x, scale, -am.x);  // train.py:178-181
+                        z4[k4].y = fmaf(x.y, scale, -am.y);
+                        z4[k4].z = fmaf(x.z, scale, -am.z);
+                        z4[k4].w = fmaf(x.w, scale, -am.w);
+                        *reinterpret_cast<float4 *>(zrow + j) = z4[k4];
+                    }
+                    m = fmaxf(m, fmaxf(fmaxf(z4[k4].x, z4[k4].y), fmaxf(z4[k4].z, z4[k4].w)));
+                }
+                m = group_max<32>(m);
+                // S = sum 2^t, W = sum 2^t * t with t = (z - m) * log2(e):  entropy = ln S - ln2 * W / S
+                // (z - m first: rows that are masked throughout sit at -1e32 and must cancel exactly)
+                float se = 0.0f, sw = 0.0f;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; k4++) {
+                    const float zz[4] = {z4[k4].x, z4[k4].y, z4[k4].z, z4[k4].w};
+#pragma unroll
+                    for (int cc = 0; cc < 4; cc++) {
+                        const float t = fmaxf((zz[cc] - m) * kLog2e, -1.0e37f);   // padding lanes / masked: 2^t == 0
+                        const float ex = fast_exp2(t);
+                        se += ex;
+                        sw = fmaf(ex, t, sw);
+                    }
+                }
+                se = group_sum<32>(se);
+                sw = group_sum<32>(sw);
+                __syncwarp();
+                if (lane == 0) {
+                    const float lsum = logf(se);
+                    finish_row(prm, L, smem, rr, grow, zrow[act], m, lsum, lsum - kLn2 * (sw / se), em, mu, scale);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(am_empty + st);
+        }
+    }
+    cp_async_wait_all();
+    HRL_STAMP(2);
+    __syncthreads();
+    HRL_STAMP(3);
+
+    float part[6];
+    targets_and_losses(prm, L, smem, c, part);
+    HRL_STAMP(4);
+    const bool last = publish_partials(prm, L, smem, c, part, &s_last);
+    if (last) finalize_losses(prm, L, smem, c);
+    HRL_STAMP(5);
+
+    // ---------------- gradients: in place, one bulk store per row
+    if (warp < NC) {
+        for (int rr = warp; rr < R; rr += NC) {
+            const int t = rr / Pa, q = rr - t * Pa;
+            const size_t grow = ((size_t)c.b0 * T0 + bi + t) * Pa + q;
+            const RowFactors f = row_factors(prm, L, smem, t, q, P, Pa);
+            const float scale = smem[L.scale + rr], m = smem[L.mx + rr], lsum = smem[L.lsum + rr], h = smem[L.ent + rr];
+            const int act = (int)s_act[rr];
+            float *zrow = smem + L.z + (size_t)rr * A;
+            // dL/draw_j = scale * (-w (1[j=a] - p_j) + k p_j (lp_j + h)) = p_j * (sk * lp_j + swk) - 1[j=a] * scale * w
+            const float sk = scale * f.k, swk = scale * (f.w + f.k * h);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) {
+                const int j = (k4 * 32 + lane) * 4;
+                if (j < A) {
+                    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (scale != 0.0f) {
+                        const float4 t4 = *reinterpret_cast<const float4 *>(zrow + j);
+                        const float zz[4] = {t4.x, t4.y, t4.z, t4.w};
+                        float g[4];
+#pragma unroll
+                        for (int cc = 0; cc < 4; cc++) {
+                            const float lp = fmaxf(zz[cc] - m - lsum, -1.0e37f);   // log-softmax, as the reference orders it
+                            const float pj = fast_exp2(lp * kLog2e);
+                            g[cc] = pj * fmaf(lp, sk, swk);
+                        }
+                        out = make_float4(g[0], g[1], g[2], g[3]);
+                    }
+                    *reinterpret_cast<float4 *>(zrow + j) = out;
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && scale != 0.0f) zrow[act] -= scale * f.w;
+            fence_proxy_async();   // generic-proxy writes -> visible to the bulk-copy engine
+            __syncwarp();
+            if (lane == 0) {
+                bulk_store(a.dpolicy_raw + grow * A, zrow, (uint32_t)A * 4);
+                if (prm.has_v) a.dvalue_raw[grow] = f.gv;
+                if (prm.has_r) a.dreturn_raw[grow] = f.gr;
+            }
+        }
+        if (lane == 0) bulk_store_wait_all();
+    }
+    zero_burn_in(prm, c);
+    HRL_STAMP(6);
+}
+
+// ======================================================================== host side
+template <typename K>
+static int launch_kernel(K kern, const LossParams &prm, int grid, int threads, size_t smem_bytes, cudaStream_t stream) {
     if (smem_bytes > 48 * 1024)
         HRL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     kern<<<grid, threads, smem_bytes, stream>>>(prm);
@@ -434,6 +507,11 @@ static int pow2_ceil(int x) {
     int p = 1;
     while (p < x) p <<= 1;
     return p;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 }  // namespace hrl
@@ -467,46 +545,98 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     prm.Tt = a.T - a.burn_in;
     prm.has_v = a.value_raw != nullptr;
     prm.has_r = a.return_raw != nullptr;
-
-    const int LPR = pow2_ceil(a.A) < 32 ? pow2_ceil(a.A) : 32;
-    const int NPL = pow2_ceil((a.A + LPR - 1) / LPR);
-    const int R = prm.Tt * a.Pa;
-    const long lanes = (long)R * LPR;
-    int threads, EPB;
-    if (lanes >= 128) {
-        EPB = 1;
-        threads = 128;
-        while (threads * 2 <= lanes && threads < 512) threads *= 2;
-    } else {
-        threads = 128;
-        EPB = (int)(128 / lanes);
-        if (EPB < 1) EPB = 1;
-        if (EPB > a.B) EPB = a.B;
-    }
-    if (threads < EPB * a.P) threads = ((EPB * a.P + 31) / 32) * 32;
-    prm.EPB = EPB;
-    const int grid = (a.B + EPB - 1) / EPB;
+    prm.n_stage = prm.chunk_rows = 0;
+    prm.trace = nullptr;
+    if (const char *e = getenv("HRL_LOSS_TRACE")) prm.trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
 
     int dev = 0, max_smem = 0;
     HRL_CUDA_CHECK(cudaGetDevice(&dev));
     HRL_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    prm.stage_z = 1;
-    SmemLayout L = make_layout(EPB, prm.Tt, a.P, a.Pa, a.A, 1);
-    if ((size_t)L.total * 4 > (size_t)max_smem - 1024) {
-        prm.stage_z = 0;
-        L = make_layout(EPB, prm.Tt, a.P, a.Pa, a.A, 0);
+    const size_t smem_cap = (size_t)max_smem - 1024;
+    const int R = prm.Tt * a.Pa;
+
+    // row mapping: one thread per row while the row fits in 16 registers, then 2..32 lanes per row
+    int LPR = 1;
+    while (LPR < 32 && (a.A + LPR - 1) / LPR > 16) LPR <<= 1;
+    const int NPL = LPR == 1 ? pow2_ceil(a.A) : 16;
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.policy_raw) & 15) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(a.action_mask) & 15) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(a.dpolicy_raw) & 15) == 0);
+    const int mode = env_int("HRL_LOSS_MODE", -1);   // -1 auto, 0 direct, 1 staged I/O, 2 bulk
+
+    // ---- bulk (TMA) kernel: wide rows
+    if (LPR == 32 && a.A % 4 == 0 && aligned16 && (mode == -1 || mode == 2)) {
+        int NC = env_int("HRL_LOSS_CONSUMERS", 16);
+        if (NC > R) NC = R;
+        if (NC > 17) NC = 17;
+        int NS = env_int("HRL_LOSS_STAGES", 3);
+        if (NS > kMaxStages) NS = kMaxStages;
+        const int nchunk = (R + NC - 1) / NC;
+        SmemLayout L = make_layout(1, prm.Tt, a.P, a.Pa, 1, a.A, NS * NC * a.A);
+        while (NS > 2 && (size_t)L.total * 4 > smem_cap) {
+            NS--;
+            L = make_layout(1, prm.Tt, a.P, a.Pa, 1, a.A, NS * NC * a.A);
+        }
+        if ((size_t)L.total * 4 <= smem_cap && nchunk <= kMaxChunks) {
+            prm.EPB = 1;
+            prm.stage_z = 1;
+            prm.row_stride = a.A;
+            prm.n_stage = NS;
+            prm.chunk_rows = NC;
+            HRL_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= 256 + (size_t)a.B * 8 * sizeof(float), HRL_ERR_WORKSPACE,
+                        "hrl_loss_fwd_bwd: workspace of %zu bytes is too small", a.workspace_bytes);
+            return launch_kernel(loss_bulk_kernel, prm, a.B, (NC + 1) * 32, (size_t)L.total * 4, stream);
+        }
+        HRL_REQUIRE(mode != 2, HRL_ERR_UNSUPPORTED, "hrl_loss_fwd_bwd: bulk kernel forced but the episode does not fit");
+    }
+
+    // ---- rows kernel
+    const long lanes = (long)R * LPR;       // lanes that have work in the row phases of one episode
+    int threads, EPB;
+    if (lanes >= 64) {
+        EPB = 1;
+        threads = 64;
+        while (threads * 2 <= lanes && threads < 256) threads *= 2;
+    } else {
+        threads = 64;
+        EPB = (int)(64 / lanes);
+        if (EPB > a.B) EPB = a.B;
+    }
+    threads = env_int("HRL_LOSS_THREADS", threads);
+    prm.EPB = EPB;
+    const int grid = (a.B + EPB - 1) / EPB;
+    const bool vec = (LPR == 32) && (a.A % 4 == 0) && aligned16;
+    // staged I/O when both the logits and the masks of the CTA's episodes fit comfortably (>= 2 CTAs per SM)
+    prm.row_stride = (LPR == 1 && a.A % 2 == 0) ? a.A + 1 : a.A;
+    const size_t io_floats = (size_t)EPB * R * prm.row_stride;
+    bool ios = !vec && (mode == -1 || mode == 1);
+    prm.stage_z = env_int("HRL_LOSS_STAGE", 1);
+    SmemLayout L = make_layout(EPB, prm.Tt, a.P, a.Pa, 1, prm.row_stride, (int)io_floats);
+    if (ios && (size_t)L.total * 4 > (mode == 1 ? smem_cap : (size_t)100 * 1024)) ios = false;
+    if (ios) {
+        prm.stage_z = 1;
+    } else {
+        prm.row_stride = a.A;
+        L = make_layout(EPB, prm.Tt, a.P, a.Pa, prm.stage_z, a.A, 0);
+        if ((size_t)L.total * 4 > smem_cap) {
+            prm.stage_z = 0;
+            L = make_layout(EPB, prm.Tt, a.P, a.Pa, 0, a.A, 0);
+        }
     }
     const size_t smem_bytes = (size_t)L.total * 4;
-    HRL_REQUIRE(smem_bytes <= (size_t)max_smem - 1024, HRL_ERR_UNSUPPORTED,
+    HRL_REQUIRE(smem_bytes <= smem_cap, HRL_ERR_UNSUPPORTED,
                 "hrl_loss_fwd_bwd: T=%d P=%d needs %zu bytes of shared memory (> %d)", a.T, a.P, smem_bytes, max_smem);
     HRL_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= 256 + (size_t)grid * 8 * sizeof(float), HRL_ERR_WORKSPACE,
                 "hrl_loss_fwd_bwd: workspace of %zu bytes is too small (need %zu)", a.workspace_bytes,
                 256 + (size_t)grid * 8 * sizeof(float));
 
-#define HRL_CASE(l, n) \
-    if (LPR == l && NPL == n) return launch<l, n>(prm, grid, threads, smem_bytes, stream);
-    HRL_CASE(1, 1) HRL_CASE(2, 1) HRL_CASE(4, 1) HRL_CASE(8, 1) HRL_CASE(16, 1) HRL_CASE(32, 1)
-    HRL_CASE(32, 2) HRL_CASE(32, 4) HRL_CASE(32, 8) HRL_CASE(32, 16)
+#define HRL_CASE(l, n, v, s) \
+    if (LPR == l && NPL == n && vec == v && ios == s) return launch_kernel(loss_rows_kernel<l, n, v, s>, prm, grid, threads, smem_bytes, stream);
+#define HRL_CASE2(l, n) HRL_CASE(l, n, false, false) HRL_CASE(l, n, false, true)
+    HRL_CASE2(1, 1) HRL_CASE2(1, 2) HRL_CASE2(1, 4) HRL_CASE2(1, 8) HRL_CASE2(1, 16)
+    HRL_CASE2(2, 16) HRL_CASE2(4, 16) HRL_CASE2(8, 16) HRL_CASE2(16, 16) HRL_CASE2(32, 16)
+    HRL_CASE(32, 16, true, false)
+#undef HRL_CASE2
 #undef HRL_CASE
     set_error("hrl_loss_fwd_bwd: no kernel for LPR=%d NPL=%d", LPR, NPL);
     return HRL_ERR_UNSUPPORTED;

@@ -277,7 +277,6 @@ class LearnerStep:
             heads.append(outs['return'])
             grads.append(buf.dreturn)
         torch.autograd.backward(heads, grads)
-        self._outs = None
         self.opt.extra_slots.copy_(buf.losses)            # the loss sums ride the gradient bucket
         if self.world > 1:
             torch.distributed.all_reduce(self.opt.flat_grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
