@@ -34,7 +34,13 @@ def _call_model(model, obs, hidden):
     return model(obs, hidden)
 
 
-def forward_raw(model, hidden, batch, args):
+def _as_format(o, memory_format):
+    if memory_format is not None and o.dim() == 4:
+        return o.contiguous(memory_format=memory_format)
+    return o
+
+
+def forward_raw(model, hidden, batch, args, memory_format=None):
     """Run the net over a batch and return its RAW outputs shaped (B, T, Pa, ...).
 
     Feed-forward nets see all B*T*Pa observations at once; recurrent nets are stepped over T
@@ -46,7 +52,7 @@ def forward_raw(model, hidden, batch, args):
     B, T, Pa = batch['action'].shape[:3]
 
     if hidden is None:
-        flat = tree_map(lambda o: o.flatten(0, 2), observations)
+        flat = tree_map(lambda o: _as_format(o.flatten(0, 2), memory_format), observations)
         outs = _call_model(model, flat, None)
         return {k: v.unflatten(0, (B, T, Pa)) for k, v in outs.items() if k != 'hidden' and v is not None}
 
@@ -55,7 +61,7 @@ def forward_raw(model, hidden, batch, args):
     per_step = {}
     omask_all = batch['observation_mask']
     for t in range(T):
-        obs_t = tree_map(lambda o: o[:, t].flatten(0, 1), observations)
+        obs_t = tree_map(lambda o: _as_format(o[:, t].flatten(0, 1), memory_format), observations)
         om = omask_all[:, t]                                                   # (B, P, 1)
 
         def gate(h):
@@ -221,10 +227,17 @@ class LearnerStep:
     """
 
     def __init__(self, model, args, example_batch, lr, device=None, process_group=None, use_graph=True,
-                 max_norm=4.0, weight_decay=1e-5, time_loss_kernel=False):
+                 max_norm=4.0, weight_decay=1e-5, time_loss_kernel=False, channels_last=True, cudnn_benchmark=True):
         self.device = torch.device(device if device is not None else 'cuda')
         self.args = args
         self.model = model.to(self.device)
+        # cuDNN's default heuristics pick FFT / NCHW-spatial kernels that are 5x slower than its NHWC
+        # implicit-GEMM kernels on the tiny boards of these games; NHWC + autotune is a pure layout choice
+        self.memory_format = torch.channels_last if channels_last else None
+        if channels_last:
+            self.model = self.model.to(memory_format=torch.channels_last)
+        if cudnn_benchmark:
+            torch.backends.cudnn.benchmark = True
         self.model.train()
         self.time_loss_kernel = time_loss_kernel
         self.kernel_events = []
@@ -257,7 +270,7 @@ class LearnerStep:
     # -- the device work of one step, on the current stream (inputs already in self.dev)
     def _part_forward(self):
         self.opt.zero_grad()
-        self._outs = forward_raw(self.model, self.hidden0, self.dev, self.args)
+        self._outs = forward_raw(self.model, self.hidden0, self.dev, self.args, self.memory_format)
         if self.loss_buf is None:
             B, T, P, Pa, A = self.dims
             self.loss_buf = ops.LossBuffers(B, T, P, Pa, A, 'value' in self._outs, 'return' in self._outs, self.device)
@@ -423,6 +436,7 @@ class Batcher:
         self.out = queue.Queue(maxsize=8)
         self.threads = []
         self.started = False
+        self.stop_event = threading.Event()
 
     def select_episode(self):
         idx, st, ed, tst = sample_window(lambda: len(self.episodes), lambda i: self.episodes[i]['steps'], self.args)
@@ -451,8 +465,15 @@ class Batcher:
 
     def _worker(self, bid):
         print('started batcher %d' % bid)
-        while True:
-            self.out.put(self._make())
+        while not self.stop_event.is_set():
+            item = self._make()
+            while not self.stop_event.is_set():
+                try:
+                    self.out.put(item, timeout=0.2)
+                    break
+                except queue.Full:
+                    continue
+        print('finished batcher %d' % bid)
 
     def run(self):
         if self.started:
@@ -464,7 +485,17 @@ class Batcher:
             self.threads.append(th)
 
     def batch(self):
-        return self.out.get()
+        while True:
+            try:
+                return self.out.get(timeout=0.2)
+            except queue.Empty:
+                if self.stop_event.is_set():
+                    return None
+
+    def stop(self):
+        self.stop_event.set()
+        for th in self.threads:
+            th.join(timeout=5)
 
 
 class Trainer:
@@ -484,6 +515,7 @@ class Trainer:
         self.update_flag = False
         self.update_queue = queue.Queue(maxsize=1)
         self.stepper = None
+        self.stop_event = threading.Event()
         if len(self.params) > 0 and not torch.cuda.is_available():
             raise RuntimeError('handyrl_b200.Trainer needs a CUDA device; there is no CPU learner in this package')
 
@@ -504,6 +536,8 @@ class Trainer:
         batch_cnt, data_cnt, loss_sum = 0, 0, {}
         while True:
             batch = self.batcher.batch()
+            if batch is None:           # stop() was called
+                return None
             if self.stepper is None:
                 self.cpu_template = copy.deepcopy(self.model)
                 self.stepper = LearnerStep(self.model, self.args, batch, self.lr)
@@ -537,10 +571,26 @@ class Trainer:
         if len(self.params) > 0:
             self.batcher.run()
             print('started training')
-        while True:
+        while not self.stop_event.is_set():
             model = self.train()
+            if model is None:
+                break
             self.update_flag = False
-            self.update_queue.put((model, self.steps))
+            while not self.stop_event.is_set():
+                try:
+                    self.update_queue.put((model, self.steps), timeout=0.2)
+                    break
+                except queue.Full:
+                    continue
+        print('finished training')
+
+    def stop(self):
+        """Not in the reference (its threads die with the process): lets tests and embedders shut the
+        trainer down cleanly -- stops the batcher threads and ends run()."""
+        self.stop_event.set()
+        self.batcher.stop()
+        if self.stepper is not None:
+            self.stepper.stream.synchronize()
 
 
 def install():

@@ -93,3 +93,6 @@ def test_trainer_thread_protocol():
     model2, steps2 = tr.update()
     assert steps2 > steps
     assert any(not torch.equal(a, b) for a, b in zip(model.state_dict().values(), model2.state_dict().values()))
+    tr.stop()
+    th.join(timeout=10)
+    assert not th.is_alive()
