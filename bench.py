@@ -285,8 +285,7 @@ def b200_arm(opt, w):
         alone = e0.elapsed_time(e1) / n_rep
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown(stepper, world)
         return
 
     peak, peak_src = measured_peak()
@@ -329,8 +328,23 @@ def b200_arm(opt, w):
                       % (r['steps'], r['B_sample'], T),
             'as_shipped_1_thread': r1['value'], 'host_cores': os.cpu_count()}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown(stepper, world)
+
+
+def shutdown(stepper, world):
+    """Tear down NCCL after the captured graphs are gone; never let a teardown hang eat the run."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    sys.stdout.flush()
+    killer = threading.Timer(20.0, lambda: os._exit(0))
+    killer.daemon = True
+    killer.start()
+    stepper.close()
+    dist.barrier()
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
+    killer.cancel()
 
 
 def main():

@@ -261,7 +261,7 @@ class LearnerStep:
         self.loss_accum = torch.zeros(NUM_LOSS, dtype=torch.float64, device=self.device)
         self.host_slots = torch.zeros((8, NUM_LOSS)).pin_memory()
         self._slot = 0
-        self.graph = None
+        self.graph = self.graph_fwd = self.graph_bwd = None
         self.use_graph = use_graph
         self.steps = 0
         self.stream = torch.cuda.Stream(device=self.device)
@@ -413,6 +413,16 @@ class LearnerStep:
         vals = self.loss_accum.cpu().tolist()
         self.loss_accum.zero_()
         return dict(zip(LOSS_KEYS, vals))
+
+    def close(self):
+        """Release the captured graphs (they pin NCCL kernels: destroy them before the process group)."""
+        self.stream.synchronize()
+        self.graph = self.graph_fwd = self.graph_bwd = None
+        self._outs = None
+        self._captured = False
+        import gc
+        gc.collect()
+        torch.cuda.synchronize(self.device)
 
     def cpu_state_dict(self):
         self.stream.synchronize()
