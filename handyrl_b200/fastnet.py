@@ -1,0 +1,115 @@
+"""Rewrite pass for nets that convolve over tiny boards (TicTacToe 3x3, Geister 6x6, ...).
+
+cuDNN has no efficient kernels for N ~ 10^4, H x W <= ~6x6: on B200 its heuristics pick FFT or
+"grouped direct" kernels that take 0.5-2 ms per layer at N = 16384 (profiles/r01_launches_*), which
+makes the user's net -- not the loss -- 97% of a learner step.  A stride-1 "same" convolution over a
+board with HW cells is exactly a dense linear map (Cin*HW -> Cout*HW) whose matrix is a fixed 0/1
+re-indexing of the kernel weights, so the layer can run as ONE cuBLAS SGEMM on the flattened
+(N, Cin*HW) activations (NCHW-contiguous, no layout change), and BatchNorm2d as two fused reductions.
+
+`optimize_small_boards(model)` swaps the class of eligible nn.Conv2d / nn.BatchNorm2d modules in place:
+parameters, buffers and state_dict keys are untouched (reference checkpoints keep loading, workers keep
+unpickling a plain nn.Module after `restore`), the arithmetic is the same fp32 multiply-adds in a
+different summation order.  Inputs whose board is larger than `max_cells` fall through to cuDNN.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+MAX_CELLS = 49
+
+
+def _selection(kh, kw, H, W, ph, pw, device, dtype):
+    """S[k, q, p] = 1 iff kernel tap k of output cell q reads input cell p (zero padding drops the rest)."""
+    S = torch.zeros(kh * kw, H * W, H * W, dtype=dtype)
+    for a in range(kh):
+        for b in range(kw):
+            for oh in range(H):
+                for ow in range(W):
+                    ih, iw = oh + a - ph, ow + b - pw
+                    if 0 <= ih < H and 0 <= iw < W:
+                        S[a * kw + b, oh * W + ow, ih * W + iw] = 1
+    return S.to(device)
+
+
+class BoardConv2d(nn.Conv2d):
+    """nn.Conv2d whose forward runs as a dense GEMM when the board is tiny."""
+
+    def _eligible(self, x):
+        kh, kw = self.kernel_size
+        return (x.dim() == 4 and x.shape[2] * x.shape[3] <= MAX_CELLS and self.stride == (1, 1)
+                and self.dilation == (1, 1) and self.groups == 1 and self.padding_mode == 'zeros'
+                and self.padding == (kh // 2, kw // 2) and kh % 2 == 1 and kw % 2 == 1)
+
+    def _sel(self, H, W, device, dtype):
+        cache = self.__dict__.setdefault('_sel_cache', {})
+        key = (H, W, device, dtype)
+        if key not in cache:
+            kh, kw = self.kernel_size
+            cache[key] = _selection(kh, kw, H, W, self.padding[0], self.padding[1], device, dtype)
+        return cache[key]
+
+    def forward(self, x):
+        if not self._eligible(x):
+            return super().forward(x)
+        N, Cin, H, W = x.shape
+        HW = H * W
+        Cout = self.out_channels
+        S = self._sel(H, W, x.device, x.dtype)                                        # (K, HW, HW)
+        # dense matrix of the layer: Wb[(o,q),(i,p)] = sum_k w[o,i,k] S[k,q,p]
+        Wb = (self.weight.reshape(Cout * Cin, -1) @ S.reshape(S.shape[0], HW * HW))
+        Wb = Wb.reshape(Cout, Cin, HW, HW).permute(0, 2, 1, 3).reshape(Cout * HW, Cin * HW)
+        y = F.linear(x.reshape(N, Cin * HW), Wb)
+        y = y.reshape(N, Cout, H, W)
+        if self.bias is not None:
+            y = y + self.bias.view(1, Cout, 1, 1)
+        return y
+
+
+class BoardBatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d with training-mode statistics as two fused reductions over (N, HW) on tiny boards
+    (cuDNN's spatial BN kernels launch one CTA per channel: ~1 ms at N=16384, C=32)."""
+
+    def forward(self, x):
+        if not (self.training and x.dim() == 4 and x.shape[2] * x.shape[3] <= MAX_CELLS and self.track_running_stats):
+            return super().forward(x)
+        N, C, H, W = x.shape
+        x3 = x.reshape(N, C, H * W)
+        var, mean = torch.var_mean(x3, dim=(0, 2), unbiased=False, keepdim=True)
+        if self.momentum is None:
+            raise NotImplementedError('cumulative moving average BatchNorm is not rewritten')
+        with torch.no_grad():
+            n = N * H * W
+            self.num_batches_tracked.add_(1)
+            self.running_mean.mul_(1 - self.momentum).add_(mean.reshape(C), alpha=self.momentum)
+            self.running_var.mul_(1 - self.momentum).add_(var.reshape(C) * (n / max(n - 1, 1)), alpha=self.momentum)
+        scale = torch.rsqrt(var + self.eps)
+        if self.affine:
+            scale = scale * self.weight.view(1, C, 1)
+            y = (x3 - mean) * scale + self.bias.view(1, C, 1)
+        else:
+            y = (x3 - mean) * scale
+        return y.reshape(N, C, H, W)
+
+
+_SWAPS = {nn.Conv2d: BoardConv2d, nn.BatchNorm2d: BoardBatchNorm2d}
+_UNSWAPS = {v: k for k, v in _SWAPS.items()}
+
+
+def optimize_small_boards(model):
+    """Swap eligible modules to their board-aware subclasses, in place.  Returns how many were swapped."""
+    n = 0
+    for m in model.modules():
+        if type(m) in _SWAPS:
+            m.__class__ = _SWAPS[type(m)]
+            n += 1
+    return n
+
+
+def restore(model):
+    """Undo optimize_small_boards (e.g. before pickling a model for CPU workers)."""
+    for m in model.modules():
+        if type(m) in _UNSWAPS:
+            m.__dict__.pop('_sel_cache', None)
+            m.__class__ = _UNSWAPS[type(m)]
+    return model

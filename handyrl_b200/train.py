@@ -23,7 +23,7 @@ from collections import deque
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, fastnet
 from .batch import tree_map, tree_leaves, make_batch, flatten_moments, decode_moments, gather_windows, sample_window
 from ._capi import LOSS_KEYS, NUM_LOSS
 
@@ -227,12 +227,17 @@ class LearnerStep:
     """
 
     def __init__(self, model, args, example_batch, lr, device=None, process_group=None, use_graph=True,
-                 max_norm=4.0, weight_decay=1e-5, time_loss_kernel=False, channels_last=True, cudnn_benchmark=True):
+                 max_norm=4.0, weight_decay=1e-5, time_loss_kernel=False, channels_last=True, cudnn_benchmark=True,
+                 small_boards=True):
         self.device = torch.device(device if device is not None else 'cuda')
         self.args = args
         self.model = model.to(self.device)
         # cuDNN's default heuristics pick FFT / NCHW-spatial kernels that are 5x slower than its NHWC
         # implicit-GEMM kernels on the tiny boards of these games; NHWC + autotune is a pure layout choice
+        # tiny boards: convolutions as one SGEMM, BatchNorm as fused reductions (fastnet.py); NCHW stays as is
+        self.rewritten = fastnet.optimize_small_boards(self.model) if small_boards else 0
+        if self.rewritten:
+            channels_last = False
         self.memory_format = torch.channels_last if channels_last else None
         if channels_last:
             self.model = self.model.to(memory_format=torch.channels_last)
@@ -426,7 +431,7 @@ class LearnerStep:
 
     def cpu_state_dict(self):
         self.stream.synchronize()
-        return {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}
+        return {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items() if not k.endswith('_sel_cache')}
 
 
 # --------------------------------------------------------------------------- batcher + trainer
