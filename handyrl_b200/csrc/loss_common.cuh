@@ -13,6 +13,7 @@ struct LossParams {
     int has_v, has_r;
     int row_stride;   // floats between consecutive rows of the staged logits (>= A)
     int n_stage, chunk_rows;   // bulk pipeline: action-mask ring depth and rows per chunk
+    int stagger_cycles;   // bulk kernel: first-wave delay of odd SMs, de-synchronises load/compute/store phases across SMs
     long long *trace;  // optional per-phase clock64 stamps of one CTA (HRL_LOSS_TRACE, debugging only)
 };
 
@@ -21,6 +22,9 @@ struct SmemLayout {
     int emask, prog;                                        // [cells]
     int tm, om, rew, ret, wterm, dv, dr;                    // [cols]
     int vb, lamv, rout, lamr, tgv, tgr, advv, advr;         // [cols] recurrence inputs / outputs
+    int coef;                                               // [4 kinds][cols] float4 recurrence coefficients
+    int rec;                                                // [4 kinds][cols] recurrence state per step
+    int se, sw, za;                                         // [rows] raw row statistics (sum exp, sum exp*d, z[action])
     int outcome;                                            // [EPB*P]
     int logp, rho, ent, mx, lsum, scale, vraw, rraw, prob;  // [rows]
     int act;                                                // [rows] int64 (2 floats each)
@@ -54,6 +58,9 @@ __host__ __device__ inline SmemLayout make_layout(int EPB, int Tt, int P, int Pa
     L.tgr = o; o += cols;
     L.advv = o; o += cols;
     L.advr = o; o += cols;
+    o = (o + 3) & ~3;
+    L.coef = o; o += 4 * 4 * cols;
+    L.rec = o; o += 4 * cols;
     L.outcome = o; o += EPB * P;
     L.logp = o; o += rows;
     L.rho = o; o += rows;
@@ -64,6 +71,9 @@ __host__ __device__ inline SmemLayout make_layout(int EPB, int Tt, int P, int Pa
     L.vraw = o; o += rows;
     L.rraw = o; o += rows;
     L.prob = o; o += rows;
+    L.se = o; o += rows;
+    L.sw = o; o += rows;
+    L.za = o; o += rows;
     o = (o + 1) & ~1;
     L.act = o; o += 2 * rows;
     o = (o + 3) & ~3;
@@ -139,65 +149,67 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 // ---------------------------------------------------------------- recurrences (losses.py:16-60)
-// One reverse-time recurrence over a column of Tt steps held in shared memory (stride st floats).
-// Only the loop-carried arithmetic lives here; inputs of step t-1 are fetched before the dependent
-// math of step t so that shared-memory latency stays off the critical path.
-__device__ __forceinline__ void run_chain(int algo, bool has_baseline, int Tt, int st, const float *__restrict__ v,
-                                          const float *__restrict__ lam, const float *__restrict__ rew, bool rew_zero,
-                                          const float *__restrict__ ret_all, float ret_const, bool ret_is_const,
-                                          float gamma, float boot, const float *__restrict__ rho, int rho_st,
-                                          float *__restrict__ tgt, float *__restrict__ adv) {
-    if (!has_baseline || algo == HRL_MC) {  // losses.py:64-66, 16-17: no recurrence
-        for (int t = 0; t < Tt; t++) {
-            const float r = ret_is_const ? ret_const : ret_all[t * st];
-            if (tgt) tgt[t * st] = r;
-            adv[t * st] = has_baseline ? r - v[t * st] : r;
-        }
-        return;
-    }
-    if (algo == HRL_TD || algo == HRL_UPGO) {  // losses.py:20-42
-        const bool up = (algo == HRL_UPGO);
-        float G = boot;
-        float v_next = v[(Tt - 1) * st], lam_next = lam[(Tt - 1) * st];
-        if (tgt) tgt[(Tt - 1) * st] = G;
-        adv[(Tt - 1) * st] = G - v_next;
-        int tp = Tt >= 2 ? Tt - 2 : 0;
-        float v_t = v[tp * st], lam_t = lam[tp * st], r_t = rew_zero ? 0.0f : rew[tp * st];
-        for (int t = Tt - 2; t >= 0; t--) {
-            tp = t >= 1 ? t - 1 : 0;
-            const float v_p = v[tp * st], lam_p = lam[tp * st], r_p = rew_zero ? 0.0f : rew[tp * st];
-            float mix = (1.0f - lam_next) * v_next + lam_next * G;
-            if (up) mix = fmaxf(v_next, mix);
-            G = r_t + gamma * mix;
-            if (tgt) tgt[t * st] = G;
-            adv[t * st] = G - v_t;
-            v_next = v_t; lam_next = lam_t;
-            v_t = v_p; lam_t = lam_p; r_t = r_p;
-        }
-        return;
-    }
-    // V-Trace, losses.py:45-60 (c-bar == rho-bar: both clip thresholds are 1, train.py:229, 237-238)
-    float v_next = boot, vs_next = boot, acc = 0.0f, lam_next = 0.0f;
-    int tp = Tt - 1;
-    float v_t = v[tp * st], lam_t = lam[tp * st], r_t = rew_zero ? 0.0f : rew[tp * st], rh_t = rho[tp * rho_st];
-    for (int t = Tt - 1; t >= 0; t--) {
-        tp = t >= 1 ? t - 1 : 0;
-        const float v_p = v[tp * st], lam_p = lam[tp * st], r_p = rew_zero ? 0.0f : rew[tp * st], rh_p = rho[tp * rho_st];
-        const float delta = rh_t * (r_t + gamma * v_next - v_t);
-        acc = (t == Tt - 1) ? delta : delta + gamma * lam_next * rh_t * acc;
-        const float vs = acc + v_t;
-        adv[t * st] = r_t + gamma * vs_next - v_t;
-        if (tgt) tgt[t * st] = vs;
-        vs_next = vs; v_next = v_t; lam_next = lam_t;
-        v_t = v_p; lam_t = lam_p; r_t = r_p; rh_t = rh_p;
-    }
-}
-
+// The time recursions are split in three: (2a) per-step coefficients, in parallel; (2b) the loop-carried
+// part only -- one FMA (V-Trace), two FMAs (TD) or two FMAs + max (UPGO) per step, one 16-byte shared-memory
+// load and one store; (2c) targets / advantages / loss terms from the recurrence state, in parallel.
+//
+//   TD / UPGO (losses.py:20-42):  G_t = r_t + g * mix,  mix = (1-l') v' + l' G_{t+1}  [UPGO: max(v', mix)]
+//        coef = { l', (1-l') v', v', r_t }      (primes: step t+1)         state: G_t
+//   V-Trace (losses.py:45-60):    acc_t = delta_t + (g l' rho_t) acc_{t+1}
+//        coef = { g l' rho_t, delta_t, -, - }                              state: acc_t   (vs_t = acc_t + v_t)
 struct CtaCtx {
     int T0, P, Pa, A, bi, Tt;
     int b0, nE, tid, nthr;
     int nrows, ncols, ncells;
+    int shP, shPa, shTt;   // log2 when the divisor is a power of two, else -1 (index math without integer division)
 };
+
+__host__ __device__ inline int log2_exact(int d) {
+    int s = 0;
+    while ((1 << s) < d) s++;
+    return (1 << s) == d ? s : -1;
+}
+__device__ __forceinline__ int fdiv(int x, int d, int sh) { return sh >= 0 ? (x >> sh) : (x / d); }
+
+
+__device__ __forceinline__ void fill_coef(int algo, float4 *coef, int Tt, int P, int t, float gamma, float v_next,
+                                          float lam_next, float r_t, float v_t, float rho_t, float boot) {
+    // coef is the column's array (stride P float4 between steps)
+    float4 c4;
+    if (algo == HRL_VTRACE) {
+        const bool last = (t == Tt - 1);
+        const float delta = rho_t * (r_t + gamma * (last ? boot : v_next) - v_t);   // losses.py:48
+        c4 = make_float4(last ? 0.0f : gamma * lam_next * rho_t, delta, 0.f, 0.f);
+    } else {
+        c4 = make_float4(lam_next, (1.0f - lam_next) * v_next, v_next, r_t);
+    }
+    coef[(size_t)t * P] = c4;
+}
+
+__device__ __forceinline__ void run_recurrence(int algo, int Tt, int P, const float4 *__restrict__ coef, float gamma,
+                                               float boot, float *__restrict__ state) {
+    if (algo == HRL_VTRACE) {
+        float acc = 0.0f;
+#pragma unroll 4
+        for (int t = Tt - 1; t >= 0; t--) {
+            const float4 c4 = coef[(size_t)t * P];
+            acc = fmaf(c4.x, acc, c4.y);
+            state[t * P] = acc;
+        }
+    } else {
+        const bool up = (algo == HRL_UPGO);
+        float G = boot;
+        state[(Tt - 1) * P] = G;
+#pragma unroll 4
+        for (int t = Tt - 2; t >= 0; t--) {
+            const float4 c4 = coef[(size_t)t * P];
+            float mix = fmaf(c4.x, G, c4.y);
+            if (up) mix = fmaxf(c4.z, mix);
+            G = fmaf(gamma, mix, c4.w);
+            state[t * P] = G;
+        }
+    }
+}
 
 // phases 2a/2b/2c: from per-row statistics (logp, rho, ent in smem) to per-cell gradient factors and the six
 // loss partial sums of this thread.  Caller must __syncthreads() before (statistics visible) and after.
@@ -205,13 +217,20 @@ __device__ __forceinline__ void targets_and_losses(const LossParams &prm, const 
                                                    float part[6]) {
     const HrlLossArgs &a = prm.a;
     const int P = c.P, Pa = c.Pa, Tt = c.Tt;
-    // ---- 2a: everything the recurrences need that is local to a cell, in parallel
+    const int vt = a.value_target, pt = a.policy_target;
+    const bool two = (pt != vt);
+    const float gam = a.gamma;
+    float4 *coef = reinterpret_cast<float4 *>(smem + L.coef);
+    const int cstride = c.ncols;   // float4 per kind
+
+    // ---- 2a.1: per-(cell, player) baselines (train.py:241-248) and lambda mixing (losses.py:71)
     const bool sym = a.two_player_zero_sum && P == 2;
     for (int i = c.tid; i < c.ncols; i += c.nthr) {
-        const int cell = i / P, p = i - cell * P;
+        const int cell = fdiv(i, P, c.shP), p = i - cell * P;
+        const int e = (c.nE == 1) ? 0 : fdiv(cell, Tt, c.shTt);
         const int q = (Pa == P) ? p : 0;
-        const int e = cell / Tt;
-        const float om = smem[L.om + i], em = smem[L.emask + cell];
+        const float em = smem[L.emask + cell];
+        const float om = smem[L.om + i];
         const float vout = smem[L.vraw + cell * Pa + q] * om;      // train.py:184
         float vb = vout, vm = om;
         if (sym) {  // train.py:243-247
@@ -222,69 +241,100 @@ __device__ __forceinline__ void targets_and_losses(const LossParams &prm, const 
             vm = fminf(fmaxf(om + omo, 0.0f), 1.0f);
         }
         smem[L.vb + i] = vb * em + smem[L.outcome + e * P + p] * (1.0f - em);   // train.py:248
-        smem[L.lamv + i] = a.lambda + (1.0f - a.lambda) * (1.0f - vm);          // losses.py:71
+        smem[L.lamv + i] = a.lambda + (1.0f - a.lambda) * (1.0f - vm);
         smem[L.rout + i] = smem[L.rraw + cell * Pa + q] * om;
         smem[L.lamr + i] = a.lambda + (1.0f - a.lambda) * (1.0f - om);
     }
     __syncthreads();
 
-    // ---- 2b: the recurrences.  job = (column, kind); kind k runs in warp k so the four kinds
-    // (value/return stream x target/advantage algorithm) proceed concurrently:
-    //   kind 0: value stream, value_target   -> tgv (+ advv when policy_target == value_target)
-    //   kind 1: return stream, value_target  -> tgr (+ advr ...)
-    //   kind 2: value stream, policy_target  -> advv      (train.py:260-262)
-    //   kind 3: return stream, policy_target -> advr
+    // ---- 2a.2: recurrence coefficients, one job per (kind, cell, player).  kinds: 0 value/value_target,
+    //            1 return/value_target, 2 value/policy_target, 3 return/policy_target (2,3 only if they differ)
+    const int nkind = two ? 4 : 2;
+    for (int job = c.tid; job < nkind * c.ncols; job += c.nthr) {
+        const int kind = job / c.ncols, i = job - kind * c.ncols;
+        const bool rs = kind & 1;
+        const int algo = (kind >= 2) ? pt : vt;
+        if (!(rs ? prm.has_r : prm.has_v) || algo == HRL_MC) continue;
+        const int cell = fdiv(i, P, c.shP), p = i - cell * P;
+        const int e = (c.nE == 1) ? 0 : fdiv(cell, Tt, c.shTt), t = cell - e * Tt;
+        const bool lastt = (t == Tt - 1);
+        const int q = (Pa == P) ? p : 0;
+        const int vb = rs ? L.rout : L.vb, lm = rs ? L.lamr : L.lamv;
+        const float v_next = lastt ? 0.0f : smem[vb + i + P], lam_next = lastt ? 0.0f : smem[lm + i + P];
+        const float boot = rs ? smem[L.ret + (e * Tt + Tt - 1) * P + p] : smem[L.outcome + e * P + p];
+        fill_coef(algo, coef + (size_t)kind * cstride + (size_t)e * Tt * P + p, Tt, P, t, rs ? gam : 1.0f, v_next, lam_next,
+                  rs ? smem[L.rew + i] : 0.0f, smem[vb + i], smem[L.rho + cell * Pa + q], boot);
+    }
+    __syncthreads();
+
+    // ---- 2b: the loop-carried part; job = (column, kind), kind k runs in warp k (kinds proceed concurrently)
     {
-        const bool two = (a.policy_target != a.value_target);
-        const int nkind = two ? 4 : 2;
         const int warp_id = c.tid >> 5, lane_id = c.tid & 31, nwarps = c.nthr >> 5;
         const int ncolumn = c.nE * P;
         for (int kind = warp_id; kind < nkind; kind += nwarps) {
-            const bool ret_stream = (kind & 1), adv_only = (kind >= 2);
-            const int algo = adv_only ? a.policy_target : a.value_target;
+            const bool rs = kind & 1;
+            const int algo = (kind >= 2) ? pt : vt;
+            if (!(rs ? prm.has_r : prm.has_v) || algo == HRL_MC) continue;
             for (int col = lane_id; col < ncolumn; col += 32) {
-                const int e = col / P, p = col - e * P;
-                const int q = (Pa == P) ? p : 0;
-                const int base = e * Tt * P + p;
-                float *tgt = adv_only ? nullptr : smem + (ret_stream ? L.tgr : L.tgv) + base;
-                float *adv = smem + (ret_stream ? L.advr : L.advv) + base;
-                // with two algorithms, kinds 0/1 only produce targets: park their advantages in dv/dr (overwritten in 2c)
-                if (two && !adv_only) adv = smem + (ret_stream ? L.dr : L.dv) + base;
-                const float *rho = smem + L.rho + e * Tt * Pa + q;
-                if (!ret_stream) {
-                    const float oc = smem[L.outcome + e * P + p];
-                    run_chain(algo, prm.has_v, Tt, P, smem + L.vb + base, smem + L.lamv + base, nullptr, true, nullptr, oc,
-                              true, 1.0f, oc, rho, Pa, tgt, adv);
-                } else {
-                    const float boot = smem[L.ret + (e * Tt + Tt - 1) * P + p];   // returns[:, -1]
-                    run_chain(algo, prm.has_r, Tt, P, smem + L.rout + base, smem + L.lamr + base, smem + L.rew + base, false,
-                              smem + L.ret + base, 0.0f, false, a.gamma, boot, rho, Pa, tgt, adv);
-                }
+                const int e = fdiv(col, P, c.shP), p = col - e * P;
+                const size_t base = (size_t)e * Tt * P + p;
+                const float boot = rs ? smem[L.ret + (e * Tt + Tt - 1) * P + p] : smem[L.outcome + e * P + p];
+                run_recurrence(algo, Tt, P, coef + (size_t)kind * cstride + base, rs ? gam : 1.0f, boot,
+                               smem + L.rec + (size_t)kind * c.ncols + base);
             }
         }
     }
     __syncthreads();
 
-    // ---- 2c: per-cell loss terms and gradient factors, in parallel
+    // ---- 2c: targets, advantages, per-cell loss terms and gradient factors, one job per (cell, player)
     float Lp = 0.f, Lv = 0.f, Lr = 0.f, Lent = 0.f, Lreg = 0.f, dcnt = 0.f;
     for (int i = c.tid; i < c.ncols; i += c.nthr) {
-        const int cell = i / P, p = i - cell * P;
+        const int cell = fdiv(i, P, c.shP), p = i - cell * P;
+        const int e = (c.nE == 1) ? 0 : fdiv(cell, Tt, c.shTt), t = cell - e * Tt;
+        const bool lastt = (t == Tt - 1);
+        const int inext = i + P;
         const int q = (Pa == P) ? p : 0, row = cell * Pa + q;
         const float om = smem[L.om + i], tm = smem[L.tm + i];
         const float rho = smem[L.rho + row];
-        const float tgv = smem[L.tgv + i], tgr = smem[L.tgr + i];
-        const float tot_adv = rho * (smem[L.advv + i] + smem[L.advr + i]);     // train.py:265
+        const float oc = smem[L.outcome + e * P + p];
+        float tg[2] = {0.f, 0.f}, ad[2] = {0.f, 0.f};
+#pragma unroll
+        for (int rs = 0; rs < 2; rs++) {
+            const bool has = rs ? prm.has_r : prm.has_v;
+            const int vbo = rs ? L.rout : L.vb;
+            const float v_t = smem[vbo + i];
+            const float r_t = rs ? smem[L.rew + i] : 0.0f, g = rs ? gam : 1.0f;
+            const float ret_t = rs ? smem[L.ret + i] : oc;
+            const float boot = rs ? smem[L.ret + (e * Tt + Tt - 1) * P + p] : oc;
+#pragma unroll
+            for (int pass = 0; pass < 2; pass++) {
+                if (pass == 1 && !two) break;
+                const int algo = pass ? pt : vt, kind = rs + 2 * pass;
+                const float *st = smem + L.rec + (size_t)kind * c.ncols;
+                float tgt, adv;
+                if (!has) { tgt = ret_t; adv = ret_t; }                                    // losses.py:64-66
+                else if (algo == HRL_MC) { tgt = ret_t; adv = ret_t - v_t; }               // losses.py:16-17
+                else if (algo == HRL_VTRACE) {
+                    tgt = st[i] + v_t;                                                     // losses.py:56
+                    const float vs_next = lastt ? boot : st[inext] + smem[vbo + inext];
+                    adv = r_t + g * vs_next - v_t;                                         // losses.py:57-58
+                } else { tgt = st[i]; adv = tgt - v_t; }
+                if (pass == 0) tg[rs] = tgt;
+                ad[rs] = adv;
+            }
+        }
+        const float tot_adv = rho * (ad[0] + ad[1]);                            // train.py:265
         smem[L.wterm + i] = tot_adv * tm;
         Lp += -smem[L.logp + row] * tot_adv * tm;                               // train.py:202
         float dv = 0.f, dr = 0.f;
         if (prm.has_v) {                                                        // train.py:204
-            const float d = smem[L.vraw + row] * om - tgv;
+            const float d = smem[L.vraw + row] * om - tg[0];
             Lv += d * d * om;
             dv = d * om * om;
         }
         if (prm.has_r) {                                                        // train.py:206 smooth_l1, beta 1
-            const float d = smem[L.rout + i] - tgr, ad = fabsf(d);
-            Lr += (ad < 1.0f ? 0.5f * d * d : ad - 0.5f) * om;
+            const float d = smem[L.rout + i] - tg[1], adf = fabsf(d);
+            Lr += (adf < 1.0f ? 0.5f * d * d : adf - 0.5f) * om;
             dr = fminf(fmaxf(d, -1.0f), 1.0f) * om * om;
         }
         smem[L.dv + i] = dv;
@@ -294,42 +344,48 @@ __device__ __forceinline__ void targets_and_losses(const LossParams &prm, const 
         Lreg += h * (1.0f - smem[L.prog + cell] * (1.0f - a.entropy_regularization_decay));   // train.py:212
         dcnt += tm;
         if (a.tap_target_value || a.tap_target_return || a.tap_advantage) {
-            const int e = cell / Tt, t = cell - e * Tt;
             const size_t gcol = ((size_t)(c.b0 + e) * c.T0 + c.bi + t) * P + p;
-            if (a.tap_target_value) a.tap_target_value[gcol] = tgv;
-            if (a.tap_target_return) a.tap_target_return[gcol] = tgr;
+            if (a.tap_target_value) a.tap_target_value[gcol] = tg[0];
+            if (a.tap_target_return) a.tap_target_return[gcol] = tg[1];
             if (a.tap_advantage) a.tap_advantage[gcol] = tot_adv;
         }
     }
     part[0] = Lp; part[1] = Lv; part[2] = Lr; part[3] = Lent; part[4] = Lreg; part[5] = dcnt;
 }
 
-// Block-reduce the six partial sums and publish them; returns (block-uniform) whether this CTA was the last
-// one to publish.  Called BEFORE the gradient phase so that the fence does not wait for the bulk of the stores.
-__device__ __forceinline__ bool publish_partials(const LossParams &prm, const SmemLayout &L, float *smem, const CtaCtx &c,
-                                                 const float part[6], bool *s_flag) {
-    const int warp = c.tid >> 5, wl = c.tid & 31, nwarp = (c.nthr + 31) >> 5;
+// Block-reduce the six partial sums into shared memory (all threads), then let ONE warp publish them while
+// the rest of the CTA goes on to the gradient phase: the fence + ticket latency is off the critical path.
+__device__ __forceinline__ void reduce_partials(const SmemLayout &L, float *smem, const CtaCtx &c, const float part[6]) {
+    const int warp = c.tid >> 5, wl = c.tid & 31;
 #pragma unroll
     for (int i = 0; i < 6; i++) {
         float v = warp_sum(part[i]);
         if (wl == 0) smem[L.red + i * 32 + warp] = v;
     }
     __syncthreads();
+}
+
+// called by one full warp; *s_flag becomes true iff this CTA was the last one to publish.
+// Lane 0 stores the six partials and takes the ticket with ONE acq_rel atomic: its own stores are ordered
+// before the ticket by the release half, no separate (slower) fence is needed.
+__device__ __forceinline__ void publish_partials(const LossParams &prm, const SmemLayout &L, const float *smem, const CtaCtx &c,
+                                                 bool *s_flag) {
+    const int lane = c.tid & 31, nwarp = (c.nthr + 31) >> 5;
     unsigned int *counter = reinterpret_cast<unsigned int *>(prm.a.workspace);
     float *partials = reinterpret_cast<float *>(reinterpret_cast<char *>(prm.a.workspace) + 256);
-    if (c.tid < 6) {
-        float v = 0.f;
-        for (int w2 = 0; w2 < nwarp; w2++) v += smem[L.red + c.tid * 32 + w2];
-        partials[(size_t)blockIdx.x * 8 + c.tid] = v;
-        __threadfence();
-    }
-    __syncwarp();
-    if (c.tid == 0) {
-        unsigned int ticket = atomicAdd(counter, 1u);
+    float v = 0.f;
+    if (lane < 6)
+        for (int w2 = 0; w2 < nwarp; w2++) v += smem[L.red + lane * 32 + w2];
+    float vals[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) vals[i] = __shfl_sync(0xffffffffu, v, i);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) __stcg(partials + (size_t)blockIdx.x * 8 + i, vals[i]);
+        unsigned int ticket;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(counter) : "memory");
         *s_flag = (ticket == gridDim.x - 1);
     }
-    __syncthreads();
-    return *s_flag;
 }
 
 // Executed by the last CTA only: fold all block partials in a fixed order (fp64) and write the scalars.
@@ -337,7 +393,6 @@ __device__ __forceinline__ void finalize_losses(const LossParams &prm, const Sme
     const int warp = c.tid >> 5, wl = c.tid & 31, nwarp = (c.nthr + 31) >> 5;
     unsigned int *counter = reinterpret_cast<unsigned int *>(prm.a.workspace);
     const float *partials = reinterpret_cast<const float *>(reinterpret_cast<const char *>(prm.a.workspace) + 256);
-    __threadfence();
     double acc[6] = {0, 0, 0, 0, 0, 0};
     for (int blk = c.tid; blk < (int)gridDim.x; blk += c.nthr) {
 #pragma unroll

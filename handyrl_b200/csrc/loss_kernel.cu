@@ -50,6 +50,7 @@ __device__ __forceinline__ CtaCtx make_ctx(const LossParams &prm) {
     c.nE = min(prm.EPB, a.B - c.b0);
     c.tid = threadIdx.x; c.nthr = blockDim.x;
     c.nrows = c.nE * c.Tt * c.Pa; c.ncols = c.nE * c.Tt * c.P; c.ncells = c.nE * c.Tt;
+    c.shP = log2_exact(c.P); c.shPa = log2_exact(c.Pa); c.shTt = log2_exact(c.Tt);
     return c;
 }
 
@@ -98,22 +99,40 @@ __device__ __forceinline__ void zero_burn_in(const LossParams &prm, const CtaCtx
     }
 }
 
-// per-row tail of the statistics pass: gather, importance ratio, taps
-__device__ __forceinline__ void finish_row(const LossParams &prm, const SmemLayout &L, float *smem, int r, size_t grow,
-                                           float za, float m, float lsum, float h, float em, float mu, float scale) {
-    const HrlLossArgs &a = prm.a;
-    const float lt = (za - m - lsum) * em;                              // train.py:232
-    const float lb = logf(fminf(fmaxf(mu, 1e-16f), 1.0f)) * em;         // train.py:231
-    const float rho = fminf(fmaxf(expf(lt - lb), 0.0f), 1.0f);          // train.py:235-238
-    smem[L.logp + r] = lt;
-    smem[L.rho + r] = rho;
-    smem[L.ent + r] = h;
+// raw per-row statistics of the softmax pass; the scalar tail (log, exp, ratio) runs later, one thread per row
+__device__ __forceinline__ void store_row_stats(const SmemLayout &L, float *smem, int r, float za, float m, float se,
+                                                float sw, float scale) {
+    smem[L.za + r] = za;
     smem[L.mx + r] = m;
-    smem[L.lsum + r] = lsum;
+    smem[L.se + r] = se;
+    smem[L.sw + r] = sw;
     smem[L.scale + r] = scale;
-    if (a.tap_logp) a.tap_logp[grow] = lt;
-    if (a.tap_rho) a.tap_rho[grow] = rho;
-    if (a.tap_entropy) a.tap_entropy[grow] = h;
+}
+
+// phase 1b: log-sum-exp, entropy, log pi(a), clipped importance ratio -- in parallel over rows
+__device__ __forceinline__ void row_epilogue(const LossParams &prm, const SmemLayout &L, float *smem, const CtaCtx &c) {
+    const HrlLossArgs &a = prm.a;
+    const int R = c.Tt * c.Pa;
+    for (int r = c.tid; r < c.nrows; r += c.nthr) {
+        const int e = (c.nE == 1) ? 0 : r / R, rr = r - e * R, t = fdiv(rr, c.Pa, c.shPa);
+        const float se = smem[L.se + r], m = smem[L.mx + r];
+        const float lsum = logf(se);
+        const float h = lsum - smem[L.sw + r] / se;                         // entropy = ln S - W / S
+        const float em = smem[L.emask + e * c.Tt + t], mu = smem[L.prob + r];
+        const float lt = (smem[L.za + r] - m - lsum) * em;                  // train.py:232
+        const float lb = logf(fminf(fmaxf(mu, 1e-16f), 1.0f)) * em;         // train.py:231
+        const float rho = fminf(fmaxf(expf(lt - lb), 0.0f), 1.0f);          // train.py:235-238
+        smem[L.logp + r] = lt;
+        smem[L.rho + r] = rho;
+        smem[L.ent + r] = h;
+        smem[L.lsum + r] = lsum;
+        if (a.tap_logp || a.tap_rho || a.tap_entropy) {
+            const size_t grow = ((size_t)(c.b0 + e) * c.T0 + c.bi) * c.Pa + rr;
+            if (a.tap_logp) a.tap_logp[grow] = lt;
+            if (a.tap_rho) a.tap_rho[grow] = rho;
+            if (a.tap_entropy) a.tap_entropy[grow] = h;
+        }
+    }
 }
 
 // ======================================================================== rows kernel
@@ -153,7 +172,7 @@ __global__ void __launch_bounds__(512) loss_rows_kernel(const LossParams prm) {
         const int r = base + grp;
         const bool valid = r < c.nrows;
         float z[NPL];
-        float scale = 0.0f, em = 0.0f, mu = 1.0f;
+        float scale = 0.0f;
         int act = 0;
         size_t grow = 0;
         if (valid) {
@@ -164,14 +183,10 @@ __global__ void __launch_bounds__(512) loss_rows_kernel(const LossParams prm) {
                 const int scell = e * Tt + t;
                 if (Pa == P) scale = smem[L.tm + scell * P + q];
                 else for (int p = 0; p < P; p++) scale += smem[L.tm + scell * P + p];   // train.py:179-180
-                em = smem[L.emask + scell];
-                mu = smem[L.prob + r];
                 act = (int)s_act[r];
             } else {
                 if (Pa == P) scale = a.turn_mask[cell * P + q];
                 else for (int p = 0; p < P; p++) scale += a.turn_mask[cell * P + p];
-                em = a.episode_mask[cell];
-                mu = a.selected_prob[grow];
                 act = (int)a.action[grow];
             }
         }
@@ -225,22 +240,21 @@ __global__ void __launch_bounds__(512) loss_rows_kernel(const LossParams prm) {
         }
         se = group_sum<LPR>(se);
         sw = group_sum<LPR>(sw);
-        if (valid && lane == 0) {
-            const float lsum = logf(se);
-            finish_row(prm, L, smem, r, grow, za, m, lsum, lsum - sw / se, em, mu, scale);
-        }
+        if (valid && lane == 0) store_row_stats(L, smem, r, za, m, se, sw, scale);
     }
     if (!IOS) cp_async_wait_all();
     HRL_STAMP(2);
     __syncthreads();
+    row_epilogue(prm, L, smem, c);
+    __syncthreads();
     HRL_STAMP(3);
 
-    // ---------------- phase 2: targets, recurrences, per-cell terms; publish the scalars
+    // ---------------- phase 2: targets, recurrences, per-cell terms; one warp publishes the scalars
     float part[6];
     targets_and_losses(prm, L, smem, c, part);
     HRL_STAMP(4);
-    const bool last = publish_partials(prm, L, smem, c, part, &s_last);
-    if (last) finalize_losses(prm, L, smem, c);
+    reduce_partials(L, smem, c, part);
+    if ((tid >> 5) == (nthr >> 5) - 1) publish_partials(prm, L, smem, c, &s_last);
     HRL_STAMP(5);
 
     // ---------------- phase 3: gradients w.r.t. the raw net outputs
@@ -311,6 +325,115 @@ __global__ void __launch_bounds__(512) loss_rows_kernel(const LossParams prm) {
         }
     }
     zero_burn_in(prm, c);
+    __syncthreads();
+    if (s_last) finalize_losses(prm, L, smem, c);
+    HRL_STAMP(6);
+}
+
+// ======================================================================== element kernel (small action spaces)
+// One thread per ELEMENT of the (rows x A) logits block of the CTA's windows: global loads and gradient stores
+// are coalesced without any staging copy, every element-wise step (masking, exp, gradient) is one short
+// dependent chain per thread, and the row-wise steps (max, sums, scalar tail) are short loops over A <= 32
+// values held in shared memory.  This is the latency-optimal mapping when a window is only a few KB.
+__global__ void __launch_bounds__(1024) loss_elem_kernel(const LossParams prm) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ bool s_last;
+    const HrlLossArgs &a = prm.a;
+    const CtaCtx c = make_ctx(prm);
+    const int P = c.P, Pa = c.Pa, A = c.A, Tt = c.Tt, T0 = c.T0, bi = c.bi, tid = c.tid, nthr = c.nthr;
+    const int R = Tt * Pa, per_ep = R * A, nelem = c.nE * per_ep;
+    const SmemLayout L = make_layout(prm.EPB, Tt, P, Pa, 1, A, prm.EPB * R * A);
+    const long long *s_act = reinterpret_cast<const long long *>(smem + L.act);
+    float *s_z = smem + L.z, *s_e = smem + L.am;
+    HRL_STAMP(0);
+
+    stage_small(prm, L, smem, c);
+
+    // ---- 1a: masked logits, one element per thread (train.py:178-181)
+    for (int i = tid; i < nelem; i += nthr) {
+        const int e = (c.nE == 1) ? 0 : i / per_ep, rem = i - e * per_ep;
+        const int rr = rem / A, t = fdiv(rr, Pa, c.shPa), q = rr - t * Pa;
+        const size_t cell = (size_t)(c.b0 + e) * T0 + bi + t;
+        float scale = 0.0f;
+        if (Pa == P) scale = a.turn_mask[cell * P + q];
+        else for (int p = 0; p < P; p++) scale += a.turn_mask[cell * P + p];
+        const size_t g = ((size_t)(c.b0 + e) * T0 + bi) * Pa * A + rem;
+        s_z[i] = ld_stream(a.policy_raw + g) * scale - ld_stream(a.action_mask + g);
+    }
+    cp_async_wait_all();
+    HRL_STAMP(1);
+    __syncthreads();
+    // ---- 1b: row max, gathered logit, scale
+    for (int r = tid; r < c.nrows; r += nthr) {
+        const float *zr = s_z + r * A;
+        float m = zr[0];
+        for (int j = 1; j < A; j++) m = fmaxf(m, zr[j]);
+        const int e = (c.nE == 1) ? 0 : r / R, rr = r - e * R, t = fdiv(rr, Pa, c.shPa), q = rr - t * Pa;
+        const int scell = e * Tt + t;
+        float scale = 0.0f;
+        if (Pa == P) scale = smem[L.tm + scell * P + q];
+        else for (int p = 0; p < P; p++) scale += smem[L.tm + scell * P + p];
+        smem[L.mx + r] = m;
+        smem[L.za + r] = zr[(int)s_act[r]];
+        smem[L.scale + r] = scale;
+    }
+    __syncthreads();
+    // ---- 1c: exponentials, one element per thread
+    for (int i = tid; i < nelem; i += nthr) {
+        const int r = i / A;
+        s_e[i] = expf(s_z[i] - smem[L.mx + r]);
+    }
+    __syncthreads();
+    // ---- 1d: row sums, then the scalar tail of the row (log-sum-exp, entropy, log pi(a), clipped ratio)
+    for (int r = tid; r < c.nrows; r += nthr) {
+        const float *zr = s_z + r * A, *er = s_e + r * A;
+        const float m = smem[L.mx + r];
+        float se = 0.0f, sw = 0.0f;
+        for (int j = 0; j < A; j++) {
+            se += er[j];
+            sw += er[j] * fmaxf(zr[j] - m, -3.0e38f);
+        }
+        smem[L.se + r] = se;
+        smem[L.sw + r] = sw;
+    }
+    __syncthreads();
+    row_epilogue(prm, L, smem, c);
+    HRL_STAMP(2);
+    __syncthreads();
+    HRL_STAMP(3);
+
+    float part[6];
+    targets_and_losses(prm, L, smem, c, part);
+    HRL_STAMP(4);
+    reduce_partials(L, smem, c, part);
+    if ((tid >> 5) == (nthr >> 5) - 1) publish_partials(prm, L, smem, c, &s_last);
+    HRL_STAMP(5);
+
+    // ---- 3a: per-row gradient factors (reusing the se / sw slots), value / return gradients
+    for (int r = tid; r < c.nrows; r += nthr) {
+        const int e = (c.nE == 1) ? 0 : r / R, rr = r - e * R, t = fdiv(rr, Pa, c.shPa), q = rr - t * Pa;
+        const RowFactors f = row_factors(prm, L, smem, e * Tt + t, q, P, Pa);
+        smem[L.se + r] = f.w;
+        smem[L.sw + r] = f.k;
+        const size_t grow = ((size_t)(c.b0 + e) * T0 + bi) * Pa + rr;
+        if (prm.has_v) a.dvalue_raw[grow] = f.gv;
+        if (prm.has_r) a.dreturn_raw[grow] = f.gr;
+    }
+    __syncthreads();
+    // ---- 3b: gradients, one element per thread, coalesced stores
+    for (int i = tid; i < nelem; i += nthr) {
+        const int e = (c.nE == 1) ? 0 : i / per_ep, rem = i - e * per_ep;
+        const int r = i / A, j = i - r * A;
+        const float scale = smem[L.scale + r];
+        float g = 0.0f;
+        if (scale != 0.0f)
+            g = grad_elem(s_z[i], j == (int)s_act[r], smem[L.mx + r], smem[L.lsum + r], smem[L.ent + r], smem[L.se + r],
+                          smem[L.sw + r], scale);
+        st_stream(a.dpolicy_raw + ((size_t)(c.b0 + e) * T0 + bi) * Pa * A + rem, g);
+    }
+    zero_burn_in(prm, c);
+    __syncthreads();
+    if (s_last) finalize_losses(prm, L, smem, c);
     HRL_STAMP(6);
 }
 
@@ -338,6 +461,16 @@ __global__ void __launch_bounds__(576, 1) loss_bulk_kernel(const LossParams prm)
     const size_t ep_off = ((size_t)c.b0 * T0 + bi) * Pa * A;   // first trained logit of this episode
     HRL_STAMP(0);
 
+    if (prm.stagger_cycles > 0 && blockIdx.x < (unsigned)kNumSM) {
+        // first wave only: odd SMs start half a period late, so that while one half of the chip streams its
+        // window in, the other half is in the compute / store phases (later waves inherit the offset)
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (smid & 1) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < prm.stagger_cycles) {}
+        }
+    }
     if (tid == 0) {
         for (int i = 0; i < nchunk; i++) mbar_init(raw_full + i, 1);
         for (int i = 0; i < NS; i++) { mbar_init(am_full + i, 1); mbar_init(am_empty + i, NC); }
@@ -372,18 +505,14 @@ __global__ void __launch_bounds__(576, 1) loss_bulk_kernel(const LossParams prm)
             const int st = ch % NS;
             const int rr = ch * G + warp;
             const bool valid = rr < R;
-            float scale = 0.0f, em = 0.0f, mu = 1.0f;
+            float scale = 0.0f;
             int act = 0;
-            size_t grow = 0;
             if (valid) {
                 const int t = rr / Pa, q = rr - t * Pa;
                 const size_t cell = (size_t)c.b0 * T0 + bi + t;
-                grow = cell * Pa + q;
                 if (Pa == P) scale = a.turn_mask[cell * P + q];
                 else for (int p = 0; p < P; p++) scale += a.turn_mask[cell * P + p];
-                em = a.episode_mask[cell];
-                mu = a.selected_prob[grow];
-                act = (int)a.action[grow];
+                act = (int)a.action[cell * Pa + q];
             }
             mbar_wait(raw_full + ch, 0);
             mbar_wait(am_full + st, (ch / NS) & 1);
@@ -425,10 +554,7 @@ __global__ void __launch_bounds__(576, 1) loss_bulk_kernel(const LossParams prm)
                 se = group_sum<32>(se);
                 sw = group_sum<32>(sw);
                 __syncwarp();
-                if (lane == 0) {
-                    const float lsum = logf(se);
-                    finish_row(prm, L, smem, rr, grow, zrow[act], m, lsum, lsum - kLn2 * (sw / se), em, mu, scale);
-                }
+                if (lane == 0) store_row_stats(L, smem, rr, zrow[act], m, se, sw * kLn2, scale);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(am_empty + st);
@@ -437,13 +563,15 @@ __global__ void __launch_bounds__(576, 1) loss_bulk_kernel(const LossParams prm)
     cp_async_wait_all();
     HRL_STAMP(2);
     __syncthreads();
+    row_epilogue(prm, L, smem, c);
+    __syncthreads();
     HRL_STAMP(3);
 
     float part[6];
     targets_and_losses(prm, L, smem, c, part);
     HRL_STAMP(4);
-    const bool last = publish_partials(prm, L, smem, c, part, &s_last);
-    if (last) finalize_losses(prm, L, smem, c);
+    reduce_partials(L, smem, c, part);
+    if (warp == NC) publish_partials(prm, L, smem, c, &s_last);   // the producer warp is idle from here on
     HRL_STAMP(5);
 
     // ---------------- gradients: in place, one bulk store per row
@@ -490,6 +618,8 @@ __global__ void __launch_bounds__(576, 1) loss_bulk_kernel(const LossParams prm)
         if (lane == 0) bulk_store_wait_all();
     }
     zero_burn_in(prm, c);
+    __syncthreads();
+    if (s_last) finalize_losses(prm, L, smem, c);
     HRL_STAMP(6);
 }
 
@@ -546,6 +676,7 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     prm.has_v = a.value_raw != nullptr;
     prm.has_r = a.return_raw != nullptr;
     prm.n_stage = prm.chunk_rows = 0;
+    prm.stagger_cycles = env_int("HRL_LOSS_STAGGER", 0);
     prm.trace = nullptr;
     if (const char *e = getenv("HRL_LOSS_TRACE")) prm.trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
 
@@ -588,6 +719,33 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
             return launch_kernel(loss_bulk_kernel, prm, a.B, (NC + 1) * 32, (size_t)L.total * 4, stream);
         }
         HRL_REQUIRE(mode != 2, HRL_ERR_UNSUPPORTED, "hrl_loss_fwd_bwd: bulk kernel forced but the episode does not fit");
+    }
+
+    // ---- element kernel: small action spaces
+    if (LPR <= 2 && (mode == -1 || mode == 3)) {
+        const int per_ep = R * a.A;
+        int EPB = per_ep >= 256 ? 1 : (256 + per_ep - 1) / per_ep;
+        if (EPB > a.B) EPB = a.B;
+        // one thread per element, but never so many that the grid needs a second wave (64 regs/thread):
+        // the CTAs are latency-bound, residency is what gives throughput
+        const int grid0 = (a.B + EPB - 1) / EPB;
+        int cap = 1024 / ((grid0 + kNumSM - 1) / kNumSM);
+        cap = cap / 32 * 32;
+        int threads = ((EPB * per_ep + 31) / 32) * 32;
+        if (threads > cap) threads = cap;
+        if (threads > 1024) threads = 1024;
+        if (threads < 64) threads = 64;
+        threads = env_int("HRL_LOSS_THREADS", threads);
+        const SmemLayout L = make_layout(EPB, prm.Tt, a.P, a.Pa, 1, a.A, EPB * per_ep);
+        if ((size_t)L.total * 4 <= (size_t)100 * 1024) {
+            prm.EPB = EPB;
+            prm.stage_z = 1;
+            prm.row_stride = a.A;
+            const int grid = (a.B + EPB - 1) / EPB;
+            HRL_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= 256 + (size_t)grid * 8 * sizeof(float), HRL_ERR_WORKSPACE,
+                        "hrl_loss_fwd_bwd: workspace of %zu bytes is too small", a.workspace_bytes);
+            return launch_kernel(loss_elem_kernel, prm, grid, threads, (size_t)L.total * 4, stream);
+        }
     }
 
     // ---- rows kernel
