@@ -181,6 +181,41 @@ def reference_arm(opt, w):
 
 # ------------------------------------------------------------------------------ B200 arm
 
+def time_loss_alone(B, T, P, A, turn_based, observation, args, device, reps):
+    """Average device time (ms) of hrl_loss_fwd_bwd launched back to back over input sets that together exceed L2."""
+    from handyrl_b200 import ops
+    from handyrl_b200.synthetic import synthetic_batch, synthetic_outputs, bytes_per_cell
+    Pa = 1 if (turn_based and not observation) else P
+    per_set = bytes_per_cell(P, Pa, A, T, 0) * B * T
+    n = max(2, min(64, int(2 * L2_BYTES / per_set) + 1))
+    sets = []
+    for i in range(n):
+        b = synthetic_batch(B, T, P, A, turn_based=turn_based, observation=observation, seed=300 + i, with_obs=False)
+        o = synthetic_outputs(b, seed=400 + i)
+        sets.append(({k: v.to(device) for k, v in o.items()}, {k: v.to(device) for k, v in b.items()},
+                     ops.LossBuffers(B, T, P, Pa, A, True, False, device)))
+    for o, b, buf in sets:
+        ops.loss_fwd_bwd(o, b, args, buffers=buf)
+    torch.cuda.synchronize()
+    # one launch per input set captured in a CUDA graph: no host launch overhead between kernels
+    side = torch.cuda.Stream(device=device)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for o, b, buf in sets:
+                ops.loss_fwd_bwd(o, b, args, buffers=buf)
+        rounds = max(1, reps // n)
+        graph.replay()
+        side.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side)
+        for _ in range(rounds):
+            graph.replay()
+        e1.record(side)
+        side.synchronize()
+    return {'ms': e0.elapsed_time(e1) / (rounds * n), 'bytes': per_set, 'sets': n}
+
+
 def b200_arm(opt, w):
     import torch.distributed as dist
     from handyrl_b200 import ops
@@ -260,29 +295,15 @@ def b200_arm(opt, w):
     stepper.loss_kernel_ms()
     e2e_value = B * T * world * opt.steps / (ms_e2e * 1e-3)
 
-    # ---- the loss kernel alone on cold inputs (ring > L2), for the roofline explanation
-    alone = None
+    # ---- the loss kernel alone on cold inputs (distinct input sets larger than L2), at the bench shape and at the
+    #      wide-row shape of configs[4]'s per-GPU shard (where an HBM roofline is physically meaningful)
+    alone, wide = None, None
     if rank == 0:
-        from handyrl_b200.synthetic import synthetic_outputs
-        outs_ring = []
-        n_alone = max(4, min(R, int(2 * L2_BYTES / max(1, B * T * A * 8)) + 1))
-        batches = [stepper.layout.views(dev_ring[i]) for i in range(n_alone)]
-        for i in range(n_alone):
-            o = synthetic_outputs({'action_mask': torch.empty(B, T, example['action_mask'].shape[2], A)}, seed=i)
-            outs_ring.append({k: v.to(device) for k, v in o.items()})
-        bufs = [ops.LossBuffers(B, T, P, example['action_mask'].shape[2], A, True, False, device) for _ in range(n_alone)]
-        for i in range(n_alone):
-            ops.loss_fwd_bwd(outs_ring[i], batches[i], args, buffers=bufs[i])
-        torch.cuda.synchronize()
-        n_rep = 200
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(n_rep):
-            j = i % n_alone
-            ops.loss_fwd_bwd(outs_ring[j], batches[j], args, buffers=bufs[j])
-        e1.record()
-        torch.cuda.synchronize()
-        alone = e0.elapsed_time(e1) / n_rep
+        alone = time_loss_alone(B, T, P, A, w['turn_based'], w['observation'], args, device, reps=200)
+        if not opt.no_wide:
+            ww = WORKLOADS['cfg5shard']
+            wide = time_loss_alone(ww['B'], ww['T'], ww['P'], ww['A'], ww['turn_based'], ww['observation'], train_args(ww),
+                                   device, reps=40)
 
     if rank != 0:
         shutdown(stepper, world)
@@ -292,10 +313,11 @@ def b200_arm(opt, w):
     Pa = example['action_mask'].shape[2]
     alg_bytes = bytes_per_cell(P, Pa, A, T, 0) * B * T
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_all = None, None
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-            traffic = json.load(f).get(opt.workload)
+            traffic_all = json.load(f)
+            traffic = traffic_all.get(opt.workload)
     except Exception:
         pass
     line = {
@@ -312,13 +334,21 @@ def b200_arm(opt, w):
                 'wall_s': wall_e2e, 'last_losses': last},
         'gpu_launches': 4 * opt.steps,          # loss fwd+bwd, grad sum-of-squares, clip+Adam, step counter
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': traffic, 'kernel': 'loss_fwd_bwd_kernel', 'kernel_us': kernel_ms * 1e3,
+                     'traffic': traffic, 'kernel': 'hrl::loss_elem_kernel (hrl_loss_fwd_bwd)', 'kernel_us': kernel_ms * 1e3,
                      'launches_timed': n_k, 'algorithmic_bytes': alg_bytes, 'peak_source': peak_src,
-                     'alone_cold_us': None if alone is None else alone * 1e3,
-                     'alone_cold_gbs': None if alone is None else alg_bytes / (alone * 1e-3) / 1e9,
-                     'note': 'event-bracketed single launch inside the step; 2.76 MB per launch is latency-bound, see DESIGN.md'},
+                     'alone_cold_us': None if alone is None else alone['ms'] * 1e3,
+                     'alone_cold_gbs': None if alone is None else alg_bytes / (alone['ms'] * 1e-3) / 1e9,
+                     'note': 'event-bracketed single launch inside the step; 2.76 MB per launch is latency-bound '
+                             '(0.42 us at peak), see DESIGN.md section 4'},
         'wall_s': wall,
     }
+    if wide is not None:
+        gbs = wide['bytes'] / (wide['ms'] * 1e-3) / 1e9
+        line['roofline_wide_rows'] = {
+            'workload': WORKLOADS['cfg5shard']['desc'] + ' (loss kernel alone, %d cold input sets)' % wide['sets'],
+            'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
+            'kernel': 'hrl::loss_bulk_kernel (hrl_loss_fwd_bwd)', 'kernel_us': wide['ms'] * 1e3,
+            'algorithmic_bytes': wide['bytes'], 'traffic': None if traffic_all is None else traffic_all.get('cfg5shard')}
     if world == 1 and not opt.no_cpu:
         r = run_cpu_port(w, steps=8, warmup=1, budget_s=25.0)
         r1 = run_cpu_port(w, steps=4, warmup=1, budget_s=12.0, threads=1)
@@ -355,6 +385,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-wide', action='store_true', help='skip the wide-row loss-kernel measurement')
     opt = ap.parse_args()
     w = WORKLOADS[opt.workload]
     if opt.impl == 'reference':
