@@ -12,8 +12,7 @@ struct LossParams {
     int stage_z;  // masked logits kept in shared memory between the statistics and the gradient phase
     int has_v, has_r;
     int row_stride;   // floats between consecutive rows of the staged logits (>= A)
-    int n_stage, chunk_rows;   // bulk pipeline: action-mask ring depth and rows per chunk
-    int stagger_cycles;   // bulk kernel: first-wave delay of odd SMs, de-synchronises load/compute/store phases across SMs
+    int cluster;          // CTAs per window (bulk kernel): 1, or 2 = thread-block cluster splitting the time axis
     long long *trace;  // optional per-phase clock64 stamps of one CTA (HRL_LOSS_TRACE, debugging only)
 };
 
@@ -21,7 +20,7 @@ struct LossParams {
 struct SmemLayout {
     int emask, prog;                                        // [cells]
     int tm, om, rew, ret, wterm, dv, dr;                    // [cols]
-    int vb, lamv, rout, lamr, tgv, tgr, advv, advr;         // [cols] recurrence inputs / outputs
+    int vb, lamv, rout, lamr;                               // [cols] recurrence inputs
     int coef;                                               // [4 kinds][cols] float4 recurrence coefficients
     int rec;                                                // [4 kinds][cols] recurrence state per step
     int se, sw, za;                                         // [rows] raw row statistics (sum exp, sum exp*d, z[action])
@@ -29,7 +28,7 @@ struct SmemLayout {
     int logp, rho, ent, mx, lsum, scale, vraw, rraw, prob;  // [rows]
     int act;                                                // [rows] int64 (2 floats each)
     int red;                                                // [8*32]
-    int bars;                                               // mbarriers (bulk pipeline), 8-byte aligned
+    int bars;                                               // mbarriers of the bulk loads, 8-byte aligned
     int z;                                                  // [rows*row_stride] if staged
     int am;                                                 // staged action mask: [rows*row_stride] or ring
     int total;
@@ -37,8 +36,10 @@ struct SmemLayout {
 
 enum { kMaxChunks = 64, kMaxStages = 8 };
 
+// alias_coef: the recurrence coefficient/state arrays (used only between the statistics and the gradient phase)
+// share storage with the action-mask ring (used only during the statistics phase)
 __host__ __device__ inline SmemLayout make_layout(int EPB, int Tt, int P, int Pa, int stage_z, int row_stride,
-                                                  int am_floats) {
+                                                  int am_floats, int z_rows = -1, bool alias_coef = false) {
     SmemLayout L;
     int cells = EPB * Tt, cols = cells * P, rows = cells * Pa, o = 0;
     L.emask = o; o += cells;
@@ -54,13 +55,6 @@ __host__ __device__ inline SmemLayout make_layout(int EPB, int Tt, int P, int Pa
     L.lamv = o; o += cols;
     L.rout = o; o += cols;
     L.lamr = o; o += cols;
-    L.tgv = o; o += cols;
-    L.tgr = o; o += cols;
-    L.advv = o; o += cols;
-    L.advr = o; o += cols;
-    o = (o + 3) & ~3;
-    L.coef = o; o += 4 * 4 * cols;
-    L.rec = o; o += 4 * cols;
     L.outcome = o; o += EPB * P;
     L.logp = o; o += rows;
     L.rho = o; o += rows;
@@ -81,10 +75,19 @@ __host__ __device__ inline SmemLayout make_layout(int EPB, int Tt, int P, int Pa
     L.bars = o; o += 2 * (kMaxChunks + 2 * kMaxStages);
     o = (o + 31) & ~31;   // 128-byte alignment for the bulk-copy destinations
     L.z = o;
-    if (stage_z) o += rows * row_stride;
+    if (stage_z) o += (z_rows >= 0 ? z_rows : rows) * row_stride;
     o = (o + 31) & ~31;
     L.am = o;
-    o += am_floats;
+    if (alias_coef && am_floats >= 20 * cols) {
+        L.coef = o;
+        L.rec = o + 16 * cols;
+        o += am_floats;
+    } else {
+        o += am_floats;
+        o = (o + 3) & ~3;
+        L.coef = o; o += 4 * 4 * cols;
+        L.rec = o; o += 4 * cols;
+    }
     L.total = o;
     return L;
 }
@@ -139,6 +142,21 @@ __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.b
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// thread-block cluster primitives (distributed shared memory)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void st_peer_f32(const float *local, uint32_t rank, float v) {
+    uint32_t addr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(addr) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // 2^x on the SFU (MUFU.EX2, max relative error 2^-22); callers fold log2(e) into the argument with one FMA
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -162,6 +180,7 @@ struct CtaCtx {
     int b0, nE, tid, nthr;
     int nrows, ncols, ncells;
     int shP, shPa, shTt;   // log2 when the divisor is a power of two, else -1 (index math without integer division)
+    int t_lo, t_hi;        // time steps whose loss terms this CTA accounts for (a cluster splits the window)
 };
 
 __host__ __device__ inline int log2_exact(int d) {
@@ -324,26 +343,27 @@ __device__ __forceinline__ void targets_and_losses(const LossParams &prm, const 
             }
         }
         const float tot_adv = rho * (ad[0] + ad[1]);                            // train.py:265
+        const float own = (t >= c.t_lo && t < c.t_hi) ? 1.0f : 0.0f;            // cluster: each cell is summed once
         smem[L.wterm + i] = tot_adv * tm;
-        Lp += -smem[L.logp + row] * tot_adv * tm;                               // train.py:202
+        Lp += own * (-smem[L.logp + row] * tot_adv * tm);                       // train.py:202
         float dv = 0.f, dr = 0.f;
         if (prm.has_v) {                                                        // train.py:204
             const float d = smem[L.vraw + row] * om - tg[0];
-            Lv += d * d * om;
+            Lv += own * (d * d * om);
             dv = d * om * om;
         }
         if (prm.has_r) {                                                        // train.py:206 smooth_l1, beta 1
             const float d = smem[L.rout + i] - tg[1], adf = fabsf(d);
-            Lr += (adf < 1.0f ? 0.5f * d * d : adf - 0.5f) * om;
+            Lr += own * ((adf < 1.0f ? 0.5f * d * d : adf - 0.5f) * om);
             dr = fminf(fmaxf(d, -1.0f), 1.0f) * om * om;
         }
         smem[L.dv + i] = dv;
         smem[L.dr + i] = dr;
         const float h = smem[L.ent + row] * tm;                                 // train.py:208
-        Lent += h;
-        Lreg += h * (1.0f - smem[L.prog + cell] * (1.0f - a.entropy_regularization_decay));   // train.py:212
-        dcnt += tm;
-        if (a.tap_target_value || a.tap_target_return || a.tap_advantage) {
+        Lent += own * h;
+        Lreg += own * (h * (1.0f - smem[L.prog + cell] * (1.0f - a.entropy_regularization_decay)));   // train.py:212
+        dcnt += own * tm;
+        if (own != 0.0f && (a.tap_target_value || a.tap_target_return || a.tap_advantage)) {
             const size_t gcol = ((size_t)(c.b0 + e) * c.T0 + c.bi + t) * P + p;
             if (a.tap_target_value) a.tap_target_value[gcol] = tg[0];
             if (a.tap_target_return) a.tap_target_return[gcol] = tg[1];
@@ -372,7 +392,7 @@ __device__ __forceinline__ void publish_partials(const LossParams &prm, const Sm
                                                  bool *s_flag) {
     const int lane = c.tid & 31, nwarp = (c.nthr + 31) >> 5;
     unsigned int *counter = reinterpret_cast<unsigned int *>(prm.a.workspace);
-    float *partials = reinterpret_cast<float *>(reinterpret_cast<char *>(prm.a.workspace) + 256);
+    float *partials = reinterpret_cast<float *>(reinterpret_cast<char *>(prm.a.workspace) + 2048);
     float v = 0.f;
     if (lane < 6)
         for (int w2 = 0; w2 < nwarp; w2++) v += smem[L.red + lane * 32 + w2];
@@ -392,7 +412,7 @@ __device__ __forceinline__ void publish_partials(const LossParams &prm, const Sm
 __device__ __forceinline__ void finalize_losses(const LossParams &prm, const SmemLayout &L, float *smem, const CtaCtx &c) {
     const int warp = c.tid >> 5, wl = c.tid & 31, nwarp = (c.nthr + 31) >> 5;
     unsigned int *counter = reinterpret_cast<unsigned int *>(prm.a.workspace);
-    const float *partials = reinterpret_cast<const float *>(reinterpret_cast<const char *>(prm.a.workspace) + 256);
+    const float *partials = reinterpret_cast<const float *>(reinterpret_cast<const char *>(prm.a.workspace) + 2048);
     double acc[6] = {0, 0, 0, 0, 0, 0};
     for (int blk = c.tid; blk < (int)gridDim.x; blk += c.nthr) {
 #pragma unroll

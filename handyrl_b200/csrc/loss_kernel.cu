@@ -18,9 +18,12 @@
 //                             rows are processed from shared memory, gradients are written back in place
 //                             and leave with one coalesced copy-out.
 //   rows kernel, direct       fallback for shapes that do not fit: coalesced (vector) global loads per row.
-//   bulk kernel               wide rows (A % 4 == 0): TMA 1-D bulk copies (cp.async.bulk + mbarrier) stream
-//                             the logits of the whole episode and a ring of action-mask chunks into shared
-//                             memory while consumer warps reduce rows; gradients leave as bulk stores.
+//   element kernel            small action spaces (A <= 32): one thread per logit, coalesced direct loads/stores,
+//                             short row-wise passes in shared memory (latency-optimal for KB-sized windows).
+//   bulk kernel               wide rows (A % 4 == 0): a 2-CTA cluster splits the window's time axis; TMA 1-D
+//                             bulk copies (cp.async.bulk + mbarrier) bring each CTA's share of the logits into
+//                             shared memory at once, warps reduce rows with register-prefetched action masks,
+//                             exchange row statistics through DSMEM; gradients leave as bulk stores.
 //
 // Phases: (0) stage  (1) per-row softmax statistics  (2a-2c) targets / recurrences / per-cell terms
 //         (publish six block partials; the last CTA folds them in a fixed order in fp64)
@@ -46,11 +49,12 @@ __device__ __forceinline__ CtaCtx make_ctx(const LossParams &prm) {
     CtaCtx c;
     const HrlLossArgs &a = prm.a;
     c.T0 = a.T; c.P = a.P; c.Pa = a.Pa; c.A = a.A; c.bi = a.burn_in; c.Tt = prm.Tt;
-    c.b0 = blockIdx.x * prm.EPB;
+    c.b0 = (prm.cluster > 1 ? blockIdx.x / prm.cluster : blockIdx.x) * prm.EPB;
     c.nE = min(prm.EPB, a.B - c.b0);
     c.tid = threadIdx.x; c.nthr = blockDim.x;
     c.nrows = c.nE * c.Tt * c.Pa; c.ncols = c.nE * c.Tt * c.P; c.ncells = c.nE * c.Tt;
     c.shP = log2_exact(c.P); c.shPa = log2_exact(c.Pa); c.shTt = log2_exact(c.Tt);
+    c.t_lo = 0; c.t_hi = c.Tt;
     return c;
 }
 
@@ -126,7 +130,7 @@ __device__ __forceinline__ void row_epilogue(const LossParams &prm, const SmemLa
         smem[L.rho + r] = rho;
         smem[L.ent + r] = h;
         smem[L.lsum + r] = lsum;
-        if (a.tap_logp || a.tap_rho || a.tap_entropy) {
+        if ((a.tap_logp || a.tap_rho || a.tap_entropy) && t >= c.t_lo && t < c.t_hi) {
             const size_t grow = ((size_t)(c.b0 + e) * c.T0 + c.bi) * c.Pa + rr;
             if (a.tap_logp) a.tap_logp[grow] = lt;
             if (a.tap_rho) a.tap_rho[grow] = rho;
@@ -438,131 +442,142 @@ __global__ void __launch_bounds__(1024) loss_elem_kernel(const LossParams prm) {
 }
 
 // ======================================================================== bulk (TMA) kernel
-// One episode per CTA, A % 4 == 0.  Warps 0..NC-1 consume rows, warp NC produces: it issues
-//   * one bulk load per chunk of `chunk_rows` logit rows into zbuf (the whole episode is in flight at once),
-//   * bulk loads of the matching action-mask chunks into an `n_stage`-deep ring, refilled as consumers release slots.
-// A consumer warp owns row (chunk * chunk_rows + warp): 32 lanes x float4 from shared memory, statistics with
-// shuffles, masked logits written back in place.  After the recurrences the same warp turns its rows into
-// gradients in place and sends each row home with a bulk store.
-__global__ void __launch_bounds__(576, 1) loss_bulk_kernel(const LossParams prm) {
+// Wide rows (A % 4 == 0).  A cluster of CS CTAs shares one window: CTA `crank` owns the time steps [t_lo, t_hi).
+//   * thread 0 issues one TMA bulk load per chunk of NC logit rows into zbuf right at the start -- the CTA's
+//     whole share (64 KB at T=64, A=512, CS=2) is in flight at once, no registers involved;
+//   * every warp owns rows warp, warp+NC, ...: it reads the action mask of its NEXT row from global memory with
+//     128-bit loads while it reduces the current row out of shared memory (one-row-ahead register prefetch),
+//     writes the masked logits back in place, and pushes the row statistics to the peer CTA through DSMEM;
+//   * after the (redundant, cheap) recurrences each warp turns its rows into gradients in place and sends every
+//     row home with a bulk store.
+// Shared memory is zbuf + ~14 KB, so two CTAs (32 row-reducing warps) share an SM.
+__global__ void __launch_bounds__(544, 2) loss_bulk_kernel(const LossParams prm) {
     extern __shared__ __align__(128) float smem[];
     __shared__ bool s_last;
     const HrlLossArgs &a = prm.a;
-    const CtaCtx c = make_ctx(prm);
+    CtaCtx c = make_ctx(prm);
     const int P = c.P, Pa = c.Pa, A = c.A, Tt = c.Tt, T0 = c.T0, bi = c.bi, tid = c.tid;
-    const int R = Tt * Pa, G = prm.chunk_rows, NS = prm.n_stage;
-    const int nchunk = (R + G - 1) / G;
-    const SmemLayout L = make_layout(1, Tt, P, Pa, 1, A, NS * G * A);
+    const int CS = prm.cluster;
+    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
+    const int Th = (Tt + CS - 1) / CS;
+    c.t_lo = min((int)crank * Th, Tt);
+    c.t_hi = min(c.t_lo + Th, Tt);
+    const int r_lo = c.t_lo * Pa, R = (c.t_hi - c.t_lo) * Pa;    // R: rows owned by this CTA
+    const int warp = tid >> 5, lane = tid & 31, NC = c.nthr >> 5;
+    const int nchunk = (R + NC - 1) / NC;
+    const SmemLayout L = make_layout(1, Tt, P, Pa, 1, A, 0, Th * Pa);
     uint64_t *raw_full = reinterpret_cast<uint64_t *>(smem + L.bars);
-    uint64_t *am_full = raw_full + kMaxChunks, *am_empty = am_full + kMaxStages;
     const long long *s_act = reinterpret_cast<const long long *>(smem + L.act);
-    const int warp = tid >> 5, lane = tid & 31;
-    const int NC = (c.nthr >> 5) - 1;   // consumer warps (== chunk_rows)
-    const size_t ep_off = ((size_t)c.b0 * T0 + bi) * Pa * A;   // first trained logit of this episode
+    const size_t ep_off = (((size_t)c.b0 * T0 + bi) * Pa + r_lo) * A;   // first logit this CTA owns
     HRL_STAMP(0);
 
-    if (prm.stagger_cycles > 0 && blockIdx.x < (unsigned)kNumSM) {
-        // first wave only: odd SMs start half a period late, so that while one half of the chip streams its
-        // window in, the other half is in the compute / store phases (later waves inherit the offset)
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        if (smid & 1) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < prm.stagger_cycles) {}
-        }
-    }
     if (tid == 0) {
         for (int i = 0; i < nchunk; i++) mbar_init(raw_full + i, 1);
-        for (int i = 0; i < NS; i++) { mbar_init(am_full + i, 1); mbar_init(am_empty + i, NC); }
         fence_mbar_init();
     }
-    __syncthreads();
-
+    // small per-cell tensors first (a few KB, cp.async) so that they do not queue behind the bulk traffic
     stage_small(prm, L, smem, c);
-
-    if (warp == NC) {
-        // ---------------- producer
-        if (lane == 0) {
-            for (int ch = 0; ch < nchunk; ch++) {
-                const int rows = min(G, R - ch * G);
-                const uint32_t bytes = (uint32_t)rows * A * 4;
-                mbar_expect_tx(raw_full + ch, bytes);
-                bulk_load(smem + L.z + (size_t)ch * G * A, a.policy_raw + ep_off + (size_t)ch * G * A, bytes, raw_full + ch);
-            }
-            for (int ch = 0; ch < nchunk; ch++) {
-                const int st = ch % NS;
-                if (ch >= NS) mbar_wait(am_empty + st, ((ch / NS) - 1) & 1);
-                const int rows = min(G, R - ch * G);
-                const uint32_t bytes = (uint32_t)rows * A * 4;
-                mbar_expect_tx(am_full + st, bytes);
-                bulk_load(smem + L.am + (size_t)st * G * A, a.action_mask + ep_off + (size_t)ch * G * A, bytes, am_full + st);
-            }
-        }
-    } else {
-        // ---------------- consumers: statistics pass.  The per-row scalars are read straight from global
-        // memory here (the staged copies only become visible CTA-wide after the barrier below).
+    __syncthreads();
+    if (tid == 0) {
         for (int ch = 0; ch < nchunk; ch++) {
-            const int st = ch % NS;
-            const int rr = ch * G + warp;
-            const bool valid = rr < R;
-            float scale = 0.0f;
-            int act = 0;
-            if (valid) {
-                const int t = rr / Pa, q = rr - t * Pa;
-                const size_t cell = (size_t)c.b0 * T0 + bi + t;
-                if (Pa == P) scale = a.turn_mask[cell * P + q];
-                else for (int p = 0; p < P; p++) scale += a.turn_mask[cell * P + p];
-                act = (int)a.action[cell * Pa + q];
-            }
-            mbar_wait(raw_full + ch, 0);
-            mbar_wait(am_full + st, (ch / NS) & 1);
-            if (valid) {
-                float *zrow = smem + L.z + (size_t)rr * A;
-                const float *arow = smem + L.am + ((size_t)st * G + warp) * A;
-                float4 z4[4];
-                float m = -INFINITY;
+            const int rows = min(NC, R - ch * NC);
+            const uint32_t bytes = (uint32_t)rows * A * 4;
+            mbar_expect_tx(raw_full + ch, bytes);
+            bulk_load(smem + L.z + (size_t)ch * NC * A, a.policy_raw + ep_off + (size_t)ch * NC * A, bytes, raw_full + ch);
+        }
+    }
+    // action mask of this warp's first row -> registers (overlaps the wait for the staged tensors)
+    float4 am_next[4];
+    {
+        const float *amp = a.action_mask + ep_off + (size_t)warp * A;
 #pragma unroll
-                for (int k4 = 0; k4 < 4; k4++) {
-                    const int j = (k4 * 32 + lane) * 4;
-                    z4[k4] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-                    if (j < A) {
-                        const float4 x = *reinterpret_cast<const float4 *>(zrow + j);
-                        const float4 am = *reinterpret_cast<const float4 *>(arow + j);
-                        z4[k4].x = fmaf(x.x, scale, -am.x);  // train.py:178-181
-                        z4[k4].y = fmaf(x.y, scale, -am.y);
-                        z4[k4].z = fmaf(x.z, scale, -am.z);
-                        z4[k4].w = fmaf(x.w, scale, -am.w);
-                        *reinterpret_cast<float4 *>(zrow + j) = z4[k4];
-                    }
-                    m = fmaxf(m, fmaxf(fmaxf(z4[k4].x, z4[k4].y), fmaxf(z4[k4].z, z4[k4].w)));
-                }
-                m = group_max<32>(m);
-                // S = sum 2^t, W = sum 2^t * t with t = (z - m) * log2(e):  entropy = ln S - ln2 * W / S
-                // (z - m first: rows that are masked throughout sit at -1e32 and must cancel exactly)
-                float se = 0.0f, sw = 0.0f;
-#pragma unroll
-                for (int k4 = 0; k4 < 4; k4++) {
-                    const float zz[4] = {z4[k4].x, z4[k4].y, z4[k4].z, z4[k4].w};
-#pragma unroll
-                    for (int cc = 0; cc < 4; cc++) {
-                        const float t = fmaxf((zz[cc] - m) * kLog2e, -1.0e37f);   // padding lanes / masked: 2^t == 0
-                        const float ex = fast_exp2(t);
-                        se += ex;
-                        sw = fmaf(ex, t, sw);
-                    }
-                }
-                se = group_sum<32>(se);
-                sw = group_sum<32>(sw);
-                __syncwarp();
-                if (lane == 0) store_row_stats(L, smem, rr, zrow[act], m, se, sw * kLn2, scale);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(am_empty + st);
+        for (int k4 = 0; k4 < 4; k4++) {
+            const int j = (k4 * 32 + lane) * 4;
+            am_next[k4] = (warp < R && j < A) ? __ldcs(reinterpret_cast<const float4 *>(amp + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     cp_async_wait_all();
+    __syncthreads();        // staged small tensors visible to every warp
+    HRL_STAMP(1);
+
+    // ---------------- statistics pass
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int rr = ch * NC + warp;              // row within this CTA's share
+        if (rr >= R) break;
+        const int gr = r_lo + rr;                   // row within the window
+        float4 am4[4];
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) am4[k4] = am_next[k4];
+        if (rr + NC < R) {                          // prefetch the next row's mask
+            const float *amp = a.action_mask + ep_off + (size_t)(rr + NC) * A;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) {
+                const int j = (k4 * 32 + lane) * 4;
+                if (j < A) am_next[k4] = __ldcs(reinterpret_cast<const float4 *>(amp + j));
+            }
+        }
+        const int t = fdiv(gr, Pa, c.shPa), q = gr - t * Pa;
+        float scale = 0.0f;
+        if (Pa == P) scale = smem[L.tm + t * P + q];
+        else for (int p = 0; p < P; p++) scale += smem[L.tm + t * P + p];   // train.py:179-180
+        const int act = (int)s_act[gr];
+        if (ch < 4) HRL_STAMP(7 + 2 * ch);
+        mbar_wait(raw_full + ch, 0);
+        if (ch < 4) HRL_STAMP(8 + 2 * ch);
+        float *zrow = smem + L.z + (size_t)rr * A;
+        // branch-free over the lane's 16 elements (indices past A are clamped and neutralised)
+        float4 z4[4];
+        float m = -INFINITY;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) {
+            const int j = (k4 * 32 + lane) * 4;
+            const bool ok = j < A;
+            const float4 x = *reinterpret_cast<const float4 *>(zrow + (ok ? j : 0));
+            z4[k4].x = ok ? fmaf(x.x, scale, -am4[k4].x) : -INFINITY;  // train.py:178-181
+            z4[k4].y = ok ? fmaf(x.y, scale, -am4[k4].y) : -INFINITY;
+            z4[k4].z = ok ? fmaf(x.z, scale, -am4[k4].z) : -INFINITY;
+            z4[k4].w = ok ? fmaf(x.w, scale, -am4[k4].w) : -INFINITY;
+            m = fmaxf(m, fmaxf(fmaxf(z4[k4].x, z4[k4].y), fmaxf(z4[k4].z, z4[k4].w)));
+        }
+        __syncwarp();       // every lane has read its raw logits before anyone overwrites them
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) {
+            const int j = (k4 * 32 + lane) * 4;
+            if (j < A) *reinterpret_cast<float4 *>(zrow + j) = z4[k4];
+        }
+        m = group_max<32>(m);
+        // S = sum 2^t, W = sum 2^t * t with t = (z - m) * log2(e):  entropy = ln S - ln2 * W / S
+        // (z - m first: rows that are masked throughout sit at -1e32 and must cancel exactly)
+        float se = 0.0f, sw = 0.0f;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) {
+            const float zz[4] = {z4[k4].x, z4[k4].y, z4[k4].z, z4[k4].w};
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                const float tt = fmaxf((zz[cc] - m) * kLog2e, -1.0e37f);   // padding lanes / masked: 2^t == 0
+                const float ex = fast_exp2(tt);
+                se += ex;
+                sw = fmaf(ex, tt, sw);
+            }
+        }
+        se = group_sum<32>(se);
+        sw = group_sum<32>(sw);
+        __syncwarp();
+        if (lane == 0) {
+            const float za = zrow[act], swn = sw * kLn2;
+            store_row_stats(L, smem, gr, za, m, se, swn, scale);
+            for (uint32_t peer = 0; peer < (uint32_t)CS; peer++) {       // the other CTA of the cluster needs them too
+                if (peer == crank) continue;
+                st_peer_f32(smem + L.za + gr, peer, za);
+                st_peer_f32(smem + L.mx + gr, peer, m);
+                st_peer_f32(smem + L.se + gr, peer, se);
+                st_peer_f32(smem + L.sw + gr, peer, swn);
+                st_peer_f32(smem + L.scale + gr, peer, scale);
+            }
+        }
+    }
     HRL_STAMP(2);
-    __syncthreads();
+    if (CS > 1) cluster_sync_all(); else __syncthreads();     // every row statistic of the window is now local
     row_epilogue(prm, L, smem, c);
     __syncthreads();
     HRL_STAMP(3);
@@ -571,53 +586,60 @@ __global__ void __launch_bounds__(576, 1) loss_bulk_kernel(const LossParams prm)
     targets_and_losses(prm, L, smem, c, part);
     HRL_STAMP(4);
     reduce_partials(L, smem, c, part);
-    if (warp == NC) publish_partials(prm, L, smem, c, &s_last);   // the producer warp is idle from here on
+    if (warp == NC - 1) publish_partials(prm, L, smem, c, &s_last);
     HRL_STAMP(5);
 
     // ---------------- gradients: in place, one bulk store per row
-    if (warp < NC) {
-        for (int rr = warp; rr < R; rr += NC) {
-            const int t = rr / Pa, q = rr - t * Pa;
-            const size_t grow = ((size_t)c.b0 * T0 + bi + t) * Pa + q;
-            const RowFactors f = row_factors(prm, L, smem, t, q, P, Pa);
-            const float scale = smem[L.scale + rr], m = smem[L.mx + rr], lsum = smem[L.lsum + rr], h = smem[L.ent + rr];
-            const int act = (int)s_act[rr];
-            float *zrow = smem + L.z + (size_t)rr * A;
-            // dL/draw_j = scale * (-w (1[j=a] - p_j) + k p_j (lp_j + h)) = p_j * (sk * lp_j + swk) - 1[j=a] * scale * w
-            const float sk = scale * f.k, swk = scale * (f.w + f.k * h);
+    for (int rr = warp; rr < R; rr += NC) {
+        const int gr = r_lo + rr;
+        const int t = fdiv(gr, Pa, c.shPa), q = gr - t * Pa;
+        const size_t grow = ((size_t)c.b0 * T0 + bi + t) * Pa + q;
+        const RowFactors f = row_factors(prm, L, smem, t, q, P, Pa);
+        const float scale = smem[L.scale + gr], m = smem[L.mx + gr], lsum = smem[L.lsum + gr], h = smem[L.ent + gr];
+        const int act = (int)s_act[gr];
+        float *zrow = smem + L.z + (size_t)rr * A;
+        // dL/draw_j = scale * (-w (1[j=a] - p_j) + k p_j (lp_j + h)) = p_j * (sk * lp_j + swk) - 1[j=a] * scale * w
+        const float sk = scale * f.k, swk = scale * (f.w + f.k * h);
+        if (scale == 0.0f) {        // warp-uniform: rows that were not the acting player's get zero gradient
 #pragma unroll
             for (int k4 = 0; k4 < 4; k4++) {
                 const int j = (k4 * 32 + lane) * 4;
-                if (j < A) {
-                    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (scale != 0.0f) {
-                        const float4 t4 = *reinterpret_cast<const float4 *>(zrow + j);
-                        const float zz[4] = {t4.x, t4.y, t4.z, t4.w};
-                        float g[4];
-#pragma unroll
-                        for (int cc = 0; cc < 4; cc++) {
-                            const float lp = fmaxf(zz[cc] - m - lsum, -1.0e37f);   // log-softmax, as the reference orders it
-                            const float pj = fast_exp2(lp * kLog2e);
-                            g[cc] = pj * fmaf(lp, sk, swk);
-                        }
-                        out = make_float4(g[0], g[1], g[2], g[3]);
-                    }
-                    *reinterpret_cast<float4 *>(zrow + j) = out;
-                }
+                if (j < A) *reinterpret_cast<float4 *>(zrow + j) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            __syncwarp();
-            if (lane == 0 && scale != 0.0f) zrow[act] -= scale * f.w;
-            fence_proxy_async();   // generic-proxy writes -> visible to the bulk-copy engine
-            __syncwarp();
-            if (lane == 0) {
-                bulk_store(a.dpolicy_raw + grow * A, zrow, (uint32_t)A * 4);
-                if (prm.has_v) a.dvalue_raw[grow] = f.gv;
-                if (prm.has_r) a.dreturn_raw[grow] = f.gr;
+        } else {
+            float4 o4[4];
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) {
+                const int j = (k4 * 32 + lane) * 4;
+                const float4 t4 = *reinterpret_cast<const float4 *>(zrow + (j < A ? j : 0));
+                const float zz[4] = {t4.x, t4.y, t4.z, t4.w};
+                float g[4];
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++) {
+                    const float lp = fmaxf(zz[cc] - m - lsum, -1.0e37f);   // log-softmax, as the reference orders it
+                    const float pj = fast_exp2(lp * kLog2e);
+                    g[cc] = pj * fmaf(lp, sk, swk);
+                }
+                o4[k4] = make_float4(g[0], g[1], g[2], g[3]);
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) {
+                const int j = (k4 * 32 + lane) * 4;
+                if (j < A) *reinterpret_cast<float4 *>(zrow + j) = o4[k4];
             }
         }
-        if (lane == 0) bulk_store_wait_all();
+        __syncwarp();
+        if (lane == 0 && scale != 0.0f) zrow[act] -= scale * f.w;
+        fence_proxy_async();   // generic-proxy writes -> visible to the bulk-copy engine
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store(a.dpolicy_raw + grow * A, zrow, (uint32_t)A * 4);
+            if (prm.has_v) a.dvalue_raw[grow] = f.gv;
+            if (prm.has_r) a.dreturn_raw[grow] = f.gr;
+        }
     }
-    zero_burn_in(prm, c);
+    if (lane == 0) bulk_store_wait_all();
+    if (crank == 0) zero_burn_in(prm, c);
     __syncthreads();
     if (s_last) finalize_losses(prm, L, smem, c);
     HRL_STAMP(6);
@@ -630,6 +652,24 @@ static int launch_kernel(K kern, const LossParams &prm, int grid, int threads, s
         HRL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     kern<<<grid, threads, smem_bytes, stream>>>(prm);
     HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
+
+static int launch_bulk(const LossParams &prm, int grid, int threads, size_t smem_bytes, cudaStream_t stream) {
+    HRL_CUDA_CHECK(cudaFuncSetAttribute(loss_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = prm.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HRL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, loss_bulk_kernel, prm));
     return HRL_OK;
 }
 
@@ -647,7 +687,7 @@ static int env_int(const char *name, int dflt) {
 }  // namespace hrl
 
 extern "C" size_t hrl_loss_workspace_bytes(int32_t B, int32_t, int32_t, int32_t, int32_t) {
-    return 256 + (size_t)(B > 0 ? B : 0) * 8 * sizeof(float);
+    return 2048 + 2 * (size_t)(B > 0 ? B : 0) * 8 * sizeof(float);   // header (ticket, per-SM arrivals) + up to two CTAs per window
 }
 
 extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
@@ -675,8 +715,7 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     prm.Tt = a.T - a.burn_in;
     prm.has_v = a.value_raw != nullptr;
     prm.has_r = a.return_raw != nullptr;
-    prm.n_stage = prm.chunk_rows = 0;
-    prm.stagger_cycles = env_int("HRL_LOSS_STAGGER", 0);
+    prm.cluster = 1;
     prm.trace = nullptr;
     if (const char *e = getenv("HRL_LOSS_TRACE")) prm.trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
 
@@ -697,28 +736,40 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
 
     // ---- bulk (TMA) kernel: wide rows
     if (LPR == 32 && a.A % 4 == 0 && aligned16 && (mode == -1 || mode == 2)) {
-        int NC = env_int("HRL_LOSS_CONSUMERS", 16);
-        if (NC > R) NC = R;
-        if (NC > 17) NC = 17;
-        int NS = env_int("HRL_LOSS_STAGES", 3);
-        if (NS > kMaxStages) NS = kMaxStages;
-        const int nchunk = (R + NC - 1) / NC;
-        SmemLayout L = make_layout(1, prm.Tt, a.P, a.Pa, 1, a.A, NS * NC * a.A);
-        while (NS > 2 && (size_t)L.total * 4 > smem_cap) {
-            NS--;
-            L = make_layout(1, prm.Tt, a.P, a.Pa, 1, a.A, NS * NC * a.A);
+        const size_t two_per_sm = 112 * 1024;     // dynamic shared memory that still lets two CTAs share an SM
+        const int force_cs = env_int("HRL_LOSS_CLUSTER", 0);
+        int NCmax = env_int("HRL_LOSS_CONSUMERS", 16);
+        if (NCmax > 17) NCmax = 17;
+        int best_cs = 0;
+        size_t best_bytes = 0;
+        // preference: (1) the whole window in one CTA if two such CTAs fit per SM; (2) a 2-CTA cluster splitting the
+        // time axis so that two CTAs fit per SM; (3) the whole window in one CTA per SM
+        for (int pass = 0; pass < 3 && !best_cs; pass++) {
+            const int cs = (pass == 1) ? 2 : 1;
+            if (force_cs && cs != force_cs) continue;
+            if (cs == 2 && prm.Tt < 2) continue;
+            const int zrows = ((prm.Tt + cs - 1) / cs) * a.Pa;
+            const SmemLayout L = make_layout(1, prm.Tt, a.P, a.Pa, 1, a.A, 0, zrows);
+            const size_t bytes = (size_t)L.total * 4;
+            const int NC = zrows < NCmax ? zrows : NCmax;
+            if (bytes <= ((pass < 2) ? two_per_sm : smem_cap) && (zrows + NC - 1) / NC <= kMaxChunks) {
+                best_cs = cs;
+                best_bytes = bytes;
+            }
         }
-        if ((size_t)L.total * 4 <= smem_cap && nchunk <= kMaxChunks) {
+        if (best_cs) {
+            const int zrows = ((prm.Tt + best_cs - 1) / best_cs) * a.Pa;
+            const int NC = zrows < NCmax ? zrows : NCmax;
             prm.EPB = 1;
             prm.stage_z = 1;
             prm.row_stride = a.A;
-            prm.n_stage = NS;
-            prm.chunk_rows = NC;
-            HRL_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= 256 + (size_t)a.B * 8 * sizeof(float), HRL_ERR_WORKSPACE,
+            prm.cluster = best_cs;
+            const int grid = a.B * best_cs;
+            HRL_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= 2048 + (size_t)grid * 8 * sizeof(float), HRL_ERR_WORKSPACE,
                         "hrl_loss_fwd_bwd: workspace of %zu bytes is too small", a.workspace_bytes);
-            return launch_kernel(loss_bulk_kernel, prm, a.B, (NC + 1) * 32, (size_t)L.total * 4, stream);
+            return launch_bulk(prm, grid, NC * 32, best_bytes, stream);
         }
-        HRL_REQUIRE(mode != 2, HRL_ERR_UNSUPPORTED, "hrl_loss_fwd_bwd: bulk kernel forced but the episode does not fit");
+        HRL_REQUIRE(mode != 2, HRL_ERR_UNSUPPORTED, "hrl_loss_fwd_bwd: bulk kernel forced but the window does not fit");
     }
 
     // ---- element kernel: small action spaces
@@ -742,7 +793,7 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
             prm.stage_z = 1;
             prm.row_stride = a.A;
             const int grid = (a.B + EPB - 1) / EPB;
-            HRL_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= 256 + (size_t)grid * 8 * sizeof(float), HRL_ERR_WORKSPACE,
+            HRL_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= 2048 + (size_t)grid * 8 * sizeof(float), HRL_ERR_WORKSPACE,
                         "hrl_loss_fwd_bwd: workspace of %zu bytes is too small", a.workspace_bytes);
             return launch_kernel(loss_elem_kernel, prm, grid, threads, (size_t)L.total * 4, stream);
         }
@@ -784,9 +835,9 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     const size_t smem_bytes = (size_t)L.total * 4;
     HRL_REQUIRE(smem_bytes <= smem_cap, HRL_ERR_UNSUPPORTED,
                 "hrl_loss_fwd_bwd: T=%d P=%d needs %zu bytes of shared memory (> %d)", a.T, a.P, smem_bytes, max_smem);
-    HRL_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= 256 + (size_t)grid * 8 * sizeof(float), HRL_ERR_WORKSPACE,
+    HRL_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= 2048 + (size_t)grid * 8 * sizeof(float), HRL_ERR_WORKSPACE,
                 "hrl_loss_fwd_bwd: workspace of %zu bytes is too small (need %zu)", a.workspace_bytes,
-                256 + (size_t)grid * 8 * sizeof(float));
+                2048 + (size_t)grid * 8 * sizeof(float));
 
 #define HRL_CASE(l, n, v, s) \
     if (LPR == l && NPL == n && vec == v && ios == s) return launch_kernel(loss_rows_kernel<l, n, v, s>, prm, grid, threads, smem_bytes, stream);

@@ -34,4 +34,4 @@ torch.cuda.synchronize()
 print(name, buf.losses.tolist())
 if os.environ.get('TRACE'):
     t = trace.cpu().tolist()
-    print('trace cycles since start:', [x - t[0] for x in t[1:7]])
+    print('trace cycles since start:', [x - t[0] for x in t[1:7]], 'consumer (wait-begin, data-ready) per chunk:', [x - t[0] for x in t[7:15]])
