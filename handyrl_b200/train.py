@@ -353,10 +353,19 @@ class LearnerStep:
     def new_packed(self):
         return PackedBatch(self.layout)
 
+    def warm_up(self):
+        """Run the warm-up steps and capture the graphs now (otherwise done lazily by the first step)."""
+        if not getattr(self, '_captured', False):
+            self._capture()
+
     def step(self, packed):
         """Enqueue H2D + one learner step for a PackedBatch; returns without waiting for the GPU.
         `packed.in_flight` tells when its host buffer may be refilled."""
         self._enqueue(packed.buffer, packed)
+
+    def step_in_place(self):
+        """Same step when the inputs were written directly into self.dev (GPU replay gather) on the step stream."""
+        self._enqueue(None, None)
 
     def step_resident(self, dev_bytes):
         """Same step with the packed batch already in HBM (e.g. produced by the replay gather kernel)."""
@@ -366,7 +375,8 @@ class LearnerStep:
         if not getattr(self, '_captured', False):
             self._capture()
         with torch.cuda.stream(self.stream):
-            self.dev_buffer.copy_(src_bytes, non_blocking=True)
+            if src_bytes is not None:
+                self.dev_buffer.copy_(src_bytes, non_blocking=True)
             if packed is not None:
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
@@ -513,14 +523,121 @@ class Batcher:
             th.join(timeout=5)
 
 
+class EpisodeDeque(deque):
+    """The `Trainer.episodes` deque the Learner appends to (train.py:472, 482-483), with a tap: every appended
+    episode is also handed to a listener (the GPU replay feeder) exactly once."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.listener = None
+
+    def append(self, ep):
+        super().append(ep)
+        if self.listener is not None:
+            self.listener(ep)
+
+    def extend(self, eps):
+        for ep in eps:
+            self.append(ep)
+
+
+class GpuBatcher:
+    """Batcher on the GPU-resident replay (replay.py + the gather/pad kernel): arriving episodes are decoded once
+    by a feeder thread and uploaded into the device ring; a batch is B window descriptors (host RNG, same sampling
+    law as Batcher.select_episode) + ONE kernel that writes straight into the learner step's input buffer."""
+
+    def __init__(self, args, episodes, device):
+        from .replay import DeviceReplay
+        self.args = args
+        self.device = device
+        cap = int(args.get('replay_capacity_steps', 0)) or min(args['maximum_episodes'] * 64, 4_000_000)
+        self.replay = DeviceReplay(cap, args['maximum_episodes'], device=device)
+        self.pending = queue.Queue()
+        self.upload_stream = torch.cuda.Stream(device=device)
+        self.last_upload = None
+        self.last_gather = None
+        self.lock = threading.Lock()
+        self.stop_event = threading.Event()
+        episodes.listener = self.pending.put        # tap first, then the backlog: nothing is missed
+        for ep in list(episodes):
+            self.pending.put(ep)
+        self.thread = threading.Thread(target=self._feed, daemon=True)
+
+    def run(self):
+        if not self.thread.is_alive():
+            self.thread.start()
+
+    def _feed(self):
+        while not self.stop_event.is_set():
+            try:
+                ep = self.pending.get(timeout=0.2)
+            except queue.Empty:
+                continue
+            fe = flatten_moments(decode_moments(ep['moment']), ep['outcome'])
+            with self.lock:
+                if self.last_gather is not None:
+                    self.last_gather.synchronize()      # never overwrite rows an in-flight gather may read
+                with torch.cuda.stream(self.upload_stream):
+                    self.replay.add_flat(fe)
+                    ev = torch.cuda.Event()
+                    ev.record(self.upload_stream)
+                    self.last_upload = ev
+
+    def ready(self):
+        return len(self.replay) > 0
+
+    def fill(self, stepper):
+        """Sample a batch and gather it into stepper.dev (on the step stream)."""
+        B = self.args['batch_size']
+        with self.lock:
+            win = self.replay.sample_windows(B, self.args)
+            with torch.cuda.stream(stepper.stream):
+                if self.last_upload is not None:
+                    stepper.stream.wait_event(self.last_upload)
+                out = dict(stepper.dev)
+                single_leaf = torch.is_tensor(stepper.dev['observation'])
+                if single_leaf:
+                    out['observation'] = stepper.dev['observation'].view(*stepper.dev['observation'].shape[:3], -1)
+                else:
+                    out['observation'] = self._flat_obs(stepper)
+                out['value'] = self._value_sink(stepper)
+                self.replay.gather(win, self.args, out=out)
+                if not single_leaf:
+                    nested = self.replay.split_observation(out['observation'])
+                    for d, s_ in zip(tree_leaves(stepper.dev['observation']), tree_leaves(nested)):
+                        d.copy_(s_)
+                ev = torch.cuda.Event()
+                ev.record(stepper.stream)
+                self.last_gather = ev
+
+    def _flat_obs(self, stepper):
+        if not hasattr(self, '_obs_buf'):
+            B, T, Pa = stepper.dev['action'].shape[:3]
+            self._obs_buf = torch.empty((B, T, Pa, self.replay.OE), device=self.device)
+        return self._obs_buf
+
+    def _value_sink(self, stepper):
+        if not hasattr(self, '_val_buf'):
+            B, T, P = stepper.dev['turn_mask'].shape[:3]
+            self._val_buf = torch.empty((B, T, P, 1), device=self.device)    # behaviour value: unused by the loss
+        return self._val_buf
+
+    def stop(self):
+        self.stop_event.set()
+        if self.thread.is_alive():
+            self.thread.join(timeout=5)
+
+
 class Trainer:
     """Drop-in for handyrl.train.Trainer (train.py:321-400): same constructor, attributes
     (`episodes`, `steps`), `run()` thread body and `update()` hand-off, same printed lines."""
 
     def __init__(self, args, model):
-        self.episodes = deque()
+        self.episodes = EpisodeDeque()
         self.args = args
         self.model = model
+        self.gpu_replay = bool(args.get('gpu_replay', True))
+        self.gpu_batcher = None
         self.default_lr = 3e-8
         self.data_cnt_ema = self.args['batch_size'] * self.args['forward_steps']
         self.params = list(self.model.parameters())
@@ -550,17 +667,33 @@ class Trainer:
             return self.model
         batch_cnt, data_cnt, loss_sum = 0, 0, {}
         while True:
-            batch = self.batcher.batch()
-            if batch is None:           # stop() was called
+            if self.stop_event.is_set():
                 return None
             if self.stepper is None:
+                # the first batch is built on the host: it fixes every shape of the captured step
+                batch = self._first_host_batch()
                 self.cpu_template = copy.deepcopy(self.model)
                 self.stepper = LearnerStep(self.model, self.args, batch, self.lr)
+                self.stepper.warm_up()
                 self.batcher.pool = [self.stepper.new_packed() for _ in range(4)]
-            packed = self.batcher.pool[batch_cnt % len(self.batcher.pool)]
-            packed.wait_reusable()
-            packed.fill(batch)
-            self.stepper.step(packed)
+                if self.gpu_replay:
+                    self.gpu_batcher = GpuBatcher(self.args, self.episodes, self.stepper.device)
+                    self.gpu_batcher.run()
+            if self.gpu_batcher is not None:
+                while not self.gpu_batcher.ready():
+                    if self.stop_event.is_set():
+                        return None
+                    time.sleep(0.01)
+                self.gpu_batcher.fill(self.stepper)
+                self.stepper.step_in_place()
+            else:
+                batch = self.batcher.batch()
+                if batch is None:           # stop() was called
+                    return None
+                packed = self.batcher.pool[batch_cnt % len(self.batcher.pool)]
+                packed.wait_reusable()
+                packed.fill(batch)
+                self.stepper.step(packed)
             batch_cnt += 1
             self.steps += 1
             if self.update_flag:            # ONE host sync per epoch instead of 4-6 per step
@@ -579,12 +712,18 @@ class Trainer:
         self.stepper.opt.set_lr(self.lr)
         return self._cpu_model()
 
+    def _first_host_batch(self):
+        return self.batcher._make()
+
     def run(self):
         print('waiting training')
         while len(self.episodes) < self.args['minimum_episodes']:
+            if self.stop_event.is_set():
+                return
             time.sleep(1)
         if len(self.params) > 0:
-            self.batcher.run()
+            if not self.gpu_replay:
+                self.batcher.run()
             print('started training')
         while not self.stop_event.is_set():
             model = self.train()
@@ -604,6 +743,8 @@ class Trainer:
         trainer down cleanly -- stops the batcher threads and ends run()."""
         self.stop_event.set()
         self.batcher.stop()
+        if self.gpu_batcher is not None:
+            self.gpu_batcher.stop()
         if self.stepper is not None:
             self.stepper.stream.synchronize()
 

@@ -75,7 +75,8 @@ def test_recurrent_compute_loss_and_param_grads(name):
         np.testing.assert_allclose(p.grad.cpu().numpy(), c['param_grads'][k], rtol=1e-3, atol=2e-5, err_msg=k)
 
 
-def test_trainer_thread_protocol():
+@pytest.mark.parametrize('gpu_replay', [True, False], ids=['gpu_replay', 'host_batcher'])
+def test_trainer_thread_protocol(gpu_replay):
     """Trainer.run() as the Learner drives it (train.py:389-400, 342-345): feed episodes, call update()."""
     import threading
     from handyrl_b200.train import Trainer
@@ -83,7 +84,8 @@ def test_trainer_thread_protocol():
     with open(os.path.join(GOLDEN, 'batch_cases.pkl'), 'rb') as f:
         case = pickle.load(f)['tictactoe']
     args = dict(case['args'], batch_size=8, minimum_episodes=4, num_batchers=1, **{'lambda': 0.7},
-                entropy_regularization=0.1, entropy_regularization_decay=0.1, policy_target='UPGO', value_target='VTRACE')
+                entropy_regularization=0.1, entropy_regularization_decay=0.1, policy_target='UPGO', value_target='VTRACE',
+                gpu_replay=gpu_replay)
     tr = Trainer(args, tictactoe_net())
     tr.episodes.extend(case['episodes'])
     th = threading.Thread(target=tr.run, daemon=True)
