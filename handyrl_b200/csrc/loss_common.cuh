@@ -266,6 +266,7 @@ __device__ __forceinline__ void targets_and_losses(const LossParams &prm, const 
     }
     __syncthreads();
 
+    if (prm.trace && blockIdx.x == gridDim.x / 2 && c.tid == 0) prm.trace[15] = clock64();
     // ---- 2a.2: recurrence coefficients, one job per (kind, cell, player).  kinds: 0 value/value_target,
     //            1 return/value_target, 2 value/policy_target, 3 return/policy_target (2,3 only if they differ)
     const int nkind = two ? 4 : 2;
@@ -286,6 +287,7 @@ __device__ __forceinline__ void targets_and_losses(const LossParams &prm, const 
     }
     __syncthreads();
 
+    if (prm.trace && blockIdx.x == gridDim.x / 2 && c.tid == 0) prm.trace[16] = clock64();
     // ---- 2b: the loop-carried part; job = (column, kind), kind k runs in warp k (kinds proceed concurrently)
     {
         const int warp_id = c.tid >> 5, lane_id = c.tid & 31, nwarps = c.nthr >> 5;
@@ -305,6 +307,7 @@ __device__ __forceinline__ void targets_and_losses(const LossParams &prm, const 
     }
     __syncthreads();
 
+    if (prm.trace && blockIdx.x == gridDim.x / 2 && c.tid == 0) prm.trace[17] = clock64();
     // ---- 2c: targets, advantages, per-cell loss terms and gradient factors, one job per (cell, player)
     float Lp = 0.f, Lv = 0.f, Lr = 0.f, Lent = 0.f, Lreg = 0.f, dcnt = 0.f;
     for (int i = c.tid; i < c.ncols; i += c.nthr) {

@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(1024) loss_elem_kernel(const LossParams prm) {
         if (prm.has_r) a.dreturn_raw[grow] = f.gr;
     }
     __syncthreads();
+    HRL_STAMP(18);
     // ---- 3b: gradients, one element per thread, coalesced stores
     for (int i = tid; i < nelem; i += nthr) {
         const int e = (c.nE == 1) ? 0 : i / per_ep, rem = i - e * per_ep;
@@ -435,6 +436,7 @@ __global__ void __launch_bounds__(1024) loss_elem_kernel(const LossParams prm) {
                           smem[L.sw + r], scale);
         st_stream(a.dpolicy_raw + ((size_t)(c.b0 + e) * T0 + bi) * Pa * A + rem, g);
     }
+    HRL_STAMP(19);
     zero_burn_in(prm, c);
     __syncthreads();
     if (s_last) finalize_losses(prm, L, smem, c);

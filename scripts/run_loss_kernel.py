@@ -18,7 +18,7 @@ o = {k: v.cuda() for k, v in o.items()}
 b = {k: v.cuda() for k, v in b.items()}
 buf = ops.LossBuffers(B, T, P, b['action_mask'].shape[2], A, True, False, 'cuda')
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
-trace = torch.zeros(16, dtype=torch.int64, device='cuda')
+trace = torch.zeros(32, dtype=torch.int64, device='cuda')
 if os.environ.get('TRACE'):
     os.environ['HRL_LOSS_TRACE'] = str(trace.data_ptr())
 mode = os.environ.get('FLUSH', 'read')
@@ -34,4 +34,4 @@ torch.cuda.synchronize()
 print(name, buf.losses.tolist())
 if os.environ.get('TRACE'):
     t = trace.cpu().tolist()
-    print('trace cycles since start:', [x - t[0] for x in t[1:7]], 'consumer (wait-begin, data-ready) per chunk:', [x - t[0] for x in t[7:15]])
+    print('trace cycles since start:', [x - t[0] for x in t[1:7]], 'consumer (wait-begin, data-ready) per chunk:', [x - t[0] for x in t[7:15]], 'phase2 (2a.2, 2b, 2c starts):', [x - t[0] for x in t[15:18]], 'phase3 (3b start, 3b end):', [x - t[0] for x in t[18:20]])
