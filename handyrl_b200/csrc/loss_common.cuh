@@ -12,6 +12,7 @@ struct LossParams {
     int stage_z;  // masked logits kept in shared memory between the statistics and the gradient phase
     int has_v, has_r;
     int row_stride;   // floats between consecutive rows of the staged logits (>= A)
+    int scan;             // recurrences as a parallel suffix scan (long windows) instead of a serial loop per column
     int cluster;          // CTAs per window (bulk kernel): 1, or 2 = thread-block cluster splitting the time axis
     long long *trace;  // optional per-phase clock64 stamps of one CTA (HRL_LOSS_TRACE, debugging only)
 };
@@ -39,7 +40,8 @@ enum { kMaxChunks = 64, kMaxStages = 8 };
 // alias_coef: the recurrence coefficient/state arrays (used only between the statistics and the gradient phase)
 // share storage with the action-mask ring (used only during the statistics phase)
 __host__ __device__ inline SmemLayout make_layout(int EPB, int Tt, int P, int Pa, int stage_z, int row_stride,
-                                                  int am_floats, int z_rows = -1, bool alias_coef = false) {
+                                                  int am_floats, int z_rows = -1, bool alias_coef = false,
+                                                  int coef_buffers = 2) {
     SmemLayout L;
     int cells = EPB * Tt, cols = cells * P, rows = cells * Pa, o = 0;
     L.emask = o; o += cells;
@@ -78,14 +80,14 @@ __host__ __device__ inline SmemLayout make_layout(int EPB, int Tt, int P, int Pa
     if (stage_z) o += (z_rows >= 0 ? z_rows : rows) * row_stride;
     o = (o + 31) & ~31;
     L.am = o;
-    if (alias_coef && am_floats >= 20 * cols) {
+    if (alias_coef && am_floats >= 36 * cols) {
         L.coef = o;
-        L.rec = o + 16 * cols;
+        L.rec = o + 32 * cols;
         o += am_floats;
     } else {
         o += am_floats;
         o = (o + 3) & ~3;
-        L.coef = o; o += 4 * 4 * cols;
+        L.coef = o; o += coef_buffers * 4 * 4 * cols;   // (two for the scan) x 4 kinds x float4
         L.rec = o; o += 4 * cols;
     }
     L.total = o;
@@ -191,6 +193,18 @@ __host__ __device__ inline int log2_exact(int d) {
 __device__ __forceinline__ int fdiv(int x, int d, int sh) { return sh >= 0 ? (x >> sh) : (x / d); }
 
 
+// Every reverse-time step of the three recurrences is a map  x -> max(a, b + c*x)  with c >= 0:
+//   TD      G_t   = r + g((1-l')v' + l' G_{t+1})            a = -big, b = r + g(1-l')v', c = g l'
+//   UPGO    G_t   = r + g max(v', (1-l')v' + l' G_{t+1})    a = r + g v', b, c as TD
+//   V-Trace acc_t = delta_t + (g l' rho_t) acc_{t+1}        a = -big, b = delta_t,       c = g l' rho_t
+// Such maps are closed under composition,
+//   (f o h)(x) = max(a_f, b_f + c_f a_h, b_f + c_f b_h + c_f c_h x),
+// so the value of every step is obtained with a parallel suffix scan over t (Kogge-Stone, log2 T rounds, one
+// thread per (kind, column, step)) instead of a T-step serial loop.  The scan reassociates the arithmetic:
+// results differ from the sequential order by a few ulp (covered by the 1e-5 parity bar, tested at full size).
+constexpr float kNegBig = -3.0e38f;
+
+// ---- serial form (default for short windows): coefficients per step, then one minimal loop per column
 __device__ __forceinline__ void fill_coef(int algo, float4 *coef, int Tt, int P, int t, float gamma, float v_next,
                                           float lam_next, float r_t, float v_t, float rho_t, float boot) {
     // coef is the column's array (stride P float4 between steps)
@@ -230,19 +244,29 @@ __device__ __forceinline__ void run_recurrence(int algo, int Tt, int P, const fl
     }
 }
 
-// phases 2a/2b/2c: from per-row statistics (logp, rho, ent in smem) to per-cell gradient factors and the six
-// loss partial sums of this thread.  Caller must __syncthreads() before (statistics visible) and after.
-__device__ __forceinline__ void targets_and_losses(const LossParams &prm, const SmemLayout &L, float *smem, const CtaCtx &c,
-                                                   float part[6]) {
+
+
+__device__ __forceinline__ float4 step_map(int algo, bool last, float gamma, float v_next, float lam_next, float r_t,
+                                           float v_t, float rho_t, float boot) {
+    if (algo == HRL_VTRACE) {
+        const float delta = rho_t * (r_t + gamma * (last ? boot : v_next) - v_t);          // losses.py:48
+        return make_float4(kNegBig, delta, last ? 0.0f : gamma * lam_next * rho_t, 0.f);    // losses.py:53
+    }
+    if (last) return make_float4(kNegBig, 0.0f, 1.0f, 0.f);                                 // identity: G_{T-1} = returns[:, -1]
+    const float b = r_t + gamma * ((1.0f - lam_next) * v_next);
+    const float a = (algo == HRL_UPGO) ? r_t + gamma * v_next : kNegBig;                    // losses.py:38
+    return make_float4(a, b, gamma * lam_next, 0.f);
+}
+
+__device__ __forceinline__ float4 compose_maps(const float4 f, const float4 h) {     // f after h
+    return make_float4(fmaxf(f.x, fmaf(f.z, h.x, f.y)), fmaf(f.z, h.y, f.y), f.z * h.z, 0.f);
+}
+
+// phase 2a: per-(cell, player) baselines (train.py:241-248) and lambda mixing (losses.py:71).  Needs only the staged
+// small tensors, so the kernels run it while the logits are still in flight; callers barrier before phase 2b.
+__device__ __forceinline__ void baselines(const LossParams &prm, const SmemLayout &L, float *smem, const CtaCtx &c) {
     const HrlLossArgs &a = prm.a;
     const int P = c.P, Pa = c.Pa, Tt = c.Tt;
-    const int vt = a.value_target, pt = a.policy_target;
-    const bool two = (pt != vt);
-    const float gam = a.gamma;
-    float4 *coef = reinterpret_cast<float4 *>(smem + L.coef);
-    const int cstride = c.ncols;   // float4 per kind
-
-    // ---- 2a.1: per-(cell, player) baselines (train.py:241-248) and lambda mixing (losses.py:71)
     const bool sym = a.two_player_zero_sum && P == 2;
     for (int i = c.tid; i < c.ncols; i += c.nthr) {
         const int cell = fdiv(i, P, c.shP), p = i - cell * P;
@@ -264,13 +288,29 @@ __device__ __forceinline__ void targets_and_losses(const LossParams &prm, const 
         smem[L.rout + i] = smem[L.rraw + cell * Pa + q] * om;
         smem[L.lamr + i] = a.lambda + (1.0f - a.lambda) * (1.0f - om);
     }
-    __syncthreads();
+}
+
+// phases 2b/2c: from per-row statistics (logp, rho, ent in smem) and the baselines of phase 2a to per-cell gradient
+// factors and the six loss partial sums of this thread.  Caller must __syncthreads() before (statistics and
+// baselines visible) and after.
+__device__ __forceinline__ void targets_and_losses(const LossParams &prm, const SmemLayout &L, float *smem, const CtaCtx &c,
+                                                   float part[6]) {
+    const HrlLossArgs &a = prm.a;
+    const int P = c.P, Pa = c.Pa, Tt = c.Tt;
+    const int vt = a.value_target, pt = a.policy_target;
+    const bool two = (pt != vt);
+    const float gam = a.gamma;
+    float4 *coef = reinterpret_cast<float4 *>(smem + L.coef);
+    const int cstride = c.ncols;   // float4 per kind
 
     if (prm.trace && blockIdx.x == gridDim.x / 2 && c.tid == 0) prm.trace[15] = clock64();
-    // ---- 2a.2: recurrence coefficients, one job per (kind, cell, player).  kinds: 0 value/value_target,
-    //            1 return/value_target, 2 value/policy_target, 3 return/policy_target (2,3 only if they differ)
+    // ---- 2b: the recurrences as a parallel suffix scan; one thread per (kind, cell, player).
+    //      kinds: 0 value/value_target, 1 return/value_target, 2 value/policy_target, 3 return/policy_target
     const int nkind = two ? 4 : 2;
-    for (int job = c.tid; job < nkind * c.ncols; job += c.nthr) {
+    const int njob = nkind * c.ncols;
+    float4 *bufA = coef, *bufB = coef + (size_t)4 * cstride;
+    int *info = reinterpret_cast<int *>(smem + L.rec);     // step index of each job during the scan (rec is written after it)
+    for (int job = c.tid; job < njob; job += c.nthr) {
         const int kind = job / c.ncols, i = job - kind * c.ncols;
         const bool rs = kind & 1;
         const int algo = (kind >= 2) ? pt : vt;
@@ -282,14 +322,18 @@ __device__ __forceinline__ void targets_and_losses(const LossParams &prm, const 
         const int vb = rs ? L.rout : L.vb, lm = rs ? L.lamr : L.lamv;
         const float v_next = lastt ? 0.0f : smem[vb + i + P], lam_next = lastt ? 0.0f : smem[lm + i + P];
         const float boot = rs ? smem[L.ret + (e * Tt + Tt - 1) * P + p] : smem[L.outcome + e * P + p];
-        fill_coef(algo, coef + (size_t)kind * cstride + (size_t)e * Tt * P + p, Tt, P, t, rs ? gam : 1.0f, v_next, lam_next,
-                  rs ? smem[L.rew + i] : 0.0f, smem[vb + i], smem[L.rho + cell * Pa + q], boot);
+        if (prm.scan) {
+            bufA[job] = step_map(algo, lastt, rs ? gam : 1.0f, v_next, lam_next, rs ? smem[L.rew + i] : 0.0f, smem[vb + i],
+                                 smem[L.rho + cell * Pa + q], boot);
+            info[job] = t;      // job table for the scan rounds: no index arithmetic inside them
+        } else {
+            fill_coef(algo, coef + (size_t)kind * cstride + (size_t)e * Tt * P + p, Tt, P, t, rs ? gam : 1.0f, v_next, lam_next,
+                      rs ? smem[L.rew + i] : 0.0f, smem[vb + i], smem[L.rho + cell * Pa + q], boot);
+        }
     }
-    __syncthreads();
-
-    if (prm.trace && blockIdx.x == gridDim.x / 2 && c.tid == 0) prm.trace[16] = clock64();
-    // ---- 2b: the loop-carried part; job = (column, kind), kind k runs in warp k (kinds proceed concurrently)
-    {
+    if (!prm.scan) {
+        __syncthreads();
+        // serial form: job = (column, kind), kind k runs in warp k (the kinds proceed concurrently)
         const int warp_id = c.tid >> 5, lane_id = c.tid & 31, nwarps = c.nthr >> 5;
         const int ncolumn = c.nE * P;
         for (int kind = warp_id; kind < nkind; kind += nwarps) {
@@ -304,8 +348,38 @@ __device__ __forceinline__ void targets_and_losses(const LossParams &prm, const 
                                smem + L.rec + (size_t)kind * c.ncols + base);
             }
         }
+        __syncthreads();
+    } else {
+    for (int job = c.tid; job < njob; job += c.nthr) {      // skipped jobs (MC / absent head) never compose
+        const int kind = job / c.ncols;
+        const int algo = (kind >= 2) ? pt : vt;
+        if (!((kind & 1) ? prm.has_r : prm.has_v) || algo == HRL_MC) info[job] = Tt;
     }
     __syncthreads();
+    if (prm.trace && blockIdx.x == gridDim.x / 2 && c.tid == 0) prm.trace[16] = clock64();
+    for (int d = 1; d < Tt; d <<= 1) {              // uniform trip count: every thread reaches every barrier
+        for (int job = c.tid; job < njob; job += c.nthr) {
+            float4 f = bufA[job];
+            if (info[job] + d < Tt) f = compose_maps(f, bufA[job + d * P]);       // same column, d steps later
+            bufB[job] = f;
+        }
+        __syncthreads();
+        float4 *tmp = bufA; bufA = bufB; bufB = tmp;
+    }
+    // the composed map of steps t..T-1 applied to the terminal value: G_t (TD/UPGO, x = returns[:, -1]) or acc_t (V-Trace, x = 0)
+    for (int job = c.tid; job < njob; job += c.nthr) {
+        const int kind = job / c.ncols, i = job - kind * c.ncols;
+        const bool rs = kind & 1;
+        const int algo = (kind >= 2) ? pt : vt;
+        if (!(rs ? prm.has_r : prm.has_v) || algo == HRL_MC) continue;
+        const int cell = fdiv(i, P, c.shP), p = i - cell * P;
+        const int e = (c.nE == 1) ? 0 : fdiv(cell, Tt, c.shTt);
+        const float x0 = (algo == HRL_VTRACE) ? 0.0f : (rs ? smem[L.ret + (e * Tt + Tt - 1) * P + p] : smem[L.outcome + e * P + p]);
+        const float4 f = bufA[job];
+        smem[L.rec + job] = fmaxf(f.x, fmaf(f.z, x0, f.y));
+    }
+    __syncthreads();
+    }   // scan
 
     if (prm.trace && blockIdx.x == gridDim.x / 2 && c.tid == 0) prm.trace[17] = clock64();
     // ---- 2c: targets, advantages, per-cell loss terms and gradient factors, one job per (cell, player)

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(512) loss_rows_kernel(const LossParams prm) {
     const CtaCtx c = make_ctx(prm);
     const int P = c.P, Pa = c.Pa, A = c.A, Tt = c.Tt, T0 = c.T0, bi = c.bi, tid = c.tid, nthr = c.nthr;
     const int R = Tt * Pa, RS = prm.row_stride;
-    const SmemLayout L = make_layout(prm.EPB, Tt, P, Pa, prm.stage_z, RS, IOS ? prm.EPB * R * RS : 0);
+    const SmemLayout L = make_layout(prm.EPB, Tt, P, Pa, prm.stage_z, RS, IOS ? prm.EPB * R * RS : 0, -1, false, prm.scan + 1);
     const long long *s_act = reinterpret_cast<const long long *>(smem + L.act);
     HRL_STAMP(0);
 
@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(512) loss_rows_kernel(const LossParams prm) {
     if (!IOS) cp_async_wait_all();
     HRL_STAMP(2);
     __syncthreads();
+    baselines(prm, L, smem, c);
     row_epilogue(prm, L, smem, c);
     __syncthreads();
     HRL_STAMP(3);
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(1024) loss_elem_kernel(const LossParams prm) {
     const CtaCtx c = make_ctx(prm);
     const int P = c.P, Pa = c.Pa, A = c.A, Tt = c.Tt, T0 = c.T0, bi = c.bi, tid = c.tid, nthr = c.nthr;
     const int R = Tt * Pa, per_ep = R * A, nelem = c.nE * per_ep;
-    const SmemLayout L = make_layout(prm.EPB, Tt, P, Pa, 1, A, prm.EPB * R * A);
+    const SmemLayout L = make_layout(prm.EPB, Tt, P, Pa, 1, A, prm.EPB * R * A, -1, false, prm.scan + 1);
     const long long *s_act = reinterpret_cast<const long long *>(smem + L.act);
     float *s_z = smem + L.z, *s_e = smem + L.am;
     HRL_STAMP(0);
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(1024) loss_elem_kernel(const LossParams prm) {
     cp_async_wait_all();
     HRL_STAMP(1);
     __syncthreads();
+    baselines(prm, L, smem, c);   // phase 2a: independent of the logits
     // ---- 1b: row max, gathered logit, scale
     for (int r = tid; r < c.nrows; r += nthr) {
         const float *zr = s_z + r * A;
@@ -467,7 +469,7 @@ __global__ void __launch_bounds__(544, 2) loss_bulk_kernel(const LossParams prm)
     const int r_lo = c.t_lo * Pa, R = (c.t_hi - c.t_lo) * Pa;    // R: rows owned by this CTA
     const int warp = tid >> 5, lane = tid & 31, NC = c.nthr >> 5;
     const int nchunk = (R + NC - 1) / NC;
-    const SmemLayout L = make_layout(1, Tt, P, Pa, 1, A, 0, Th * Pa);
+    const SmemLayout L = make_layout(1, Tt, P, Pa, 1, A, 0, Th * Pa, false, prm.scan + 1);
     uint64_t *raw_full = reinterpret_cast<uint64_t *>(smem + L.bars);
     const long long *s_act = reinterpret_cast<const long long *>(smem + L.act);
     const size_t ep_off = (((size_t)c.b0 * T0 + bi) * Pa + r_lo) * A;   // first logit this CTA owns
@@ -500,6 +502,7 @@ __global__ void __launch_bounds__(544, 2) loss_bulk_kernel(const LossParams prm)
     }
     cp_async_wait_all();
     __syncthreads();        // staged small tensors visible to every warp
+    baselines(prm, L, smem, c);   // phase 2a, while the logits are still in flight
     HRL_STAMP(1);
 
     // ---------------- statistics pass
@@ -718,6 +721,7 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     prm.has_v = a.value_raw != nullptr;
     prm.has_r = a.return_raw != nullptr;
     prm.cluster = 1;
+    prm.scan = env_int("HRL_LOSS_SCAN", prm.Tt >= 96 ? 1 : 0);   // serial recurrences win below ~100 steps
     prm.trace = nullptr;
     if (const char *e = getenv("HRL_LOSS_TRACE")) prm.trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
 
@@ -747,11 +751,14 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
         // preference: (1) the whole window in one CTA if two such CTAs fit per SM; (2) a 2-CTA cluster splitting the
         // time axis so that two CTAs fit per SM; (3) the whole window in one CTA per SM
         for (int pass = 0; pass < 3 && !best_cs; pass++) {
-            const int cs = (pass == 1) ? 2 : 1;
-            if (force_cs && cs != force_cs) continue;
-            if (cs == 2 && prm.Tt < 2) continue;
+            int cs = (pass == 1) ? 2 : 1;
+            if (force_cs) {                       // tuning override (1, 2, 4 or 8 CTAs per window)
+                if (pass != 1) continue;
+                cs = force_cs;
+            }
+            if (cs > 1 && prm.Tt < cs) continue;
             const int zrows = ((prm.Tt + cs - 1) / cs) * a.Pa;
-            const SmemLayout L = make_layout(1, prm.Tt, a.P, a.Pa, 1, a.A, 0, zrows);
+            const SmemLayout L = make_layout(1, prm.Tt, a.P, a.Pa, 1, a.A, 0, zrows, false, prm.scan + 1);
             const size_t bytes = (size_t)L.total * 4;
             const int NC = zrows < NCmax ? zrows : NCmax;
             if (bytes <= ((pass < 2) ? two_per_sm : smem_cap) && (zrows + NC - 1) / NC <= kMaxChunks) {
@@ -789,7 +796,7 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
         if (threads > 1024) threads = 1024;
         if (threads < 64) threads = 64;
         threads = env_int("HRL_LOSS_THREADS", threads);
-        const SmemLayout L = make_layout(EPB, prm.Tt, a.P, a.Pa, 1, a.A, EPB * per_ep);
+        const SmemLayout L = make_layout(EPB, prm.Tt, a.P, a.Pa, 1, a.A, EPB * per_ep, -1, false, prm.scan + 1);
         if ((size_t)L.total * 4 <= (size_t)100 * 1024) {
             prm.EPB = EPB;
             prm.stage_z = 1;
@@ -822,16 +829,16 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     const size_t io_floats = (size_t)EPB * R * prm.row_stride;
     bool ios = !vec && (mode == -1 || mode == 1);
     prm.stage_z = env_int("HRL_LOSS_STAGE", 1);
-    SmemLayout L = make_layout(EPB, prm.Tt, a.P, a.Pa, 1, prm.row_stride, (int)io_floats);
+    SmemLayout L = make_layout(EPB, prm.Tt, a.P, a.Pa, 1, prm.row_stride, (int)io_floats, -1, false, prm.scan + 1);
     if (ios && (size_t)L.total * 4 > (mode == 1 ? smem_cap : (size_t)100 * 1024)) ios = false;
     if (ios) {
         prm.stage_z = 1;
     } else {
         prm.row_stride = a.A;
-        L = make_layout(EPB, prm.Tt, a.P, a.Pa, prm.stage_z, a.A, 0);
+        L = make_layout(EPB, prm.Tt, a.P, a.Pa, prm.stage_z, a.A, 0, -1, false, prm.scan + 1);
         if ((size_t)L.total * 4 > smem_cap) {
             prm.stage_z = 0;
-            L = make_layout(EPB, prm.Tt, a.P, a.Pa, 0, a.A, 0);
+            L = make_layout(EPB, prm.Tt, a.P, a.Pa, 0, a.A, 0, -1, false, prm.scan + 1);
         }
     }
     const size_t smem_bytes = (size_t)L.total * 4;

@@ -157,3 +157,24 @@ def test_bad_arguments_fail_loudly():
     with pytest.raises(_capi.HrlError):   # burn-in swallowing the whole window
         ops.loss_fwd_bwd({k: v.cuda() for k, v in outs.items()}, {k: v.cuda() for k, v in batch.items()},
                          dict(args, burn_in_steps=6))
+
+
+@pytest.mark.parametrize('scan', ['0', '1'], ids=['serial', 'scan'])
+@pytest.mark.parametrize('name', ['alt_UPGO_VTRACE', 'sim_TD_UPGO', 'obs_VTRACE_TD', 'alt_MC_UPGO', 'long', 'burnin_alt', 'alt4', 'wide512'])
+def test_both_recurrence_forms_match_reference(name, scan, monkeypatch):
+    """The serial per-column loops (default for short windows) and the parallel suffix scan of max-affine maps
+    (default for T >= 96) must both reproduce the reference."""
+    from handyrl_b200 import ops
+    monkeypatch.setenv('HRL_LOSS_SCAN', scan)
+    case = LOSS_CASES[name]
+    batch, outs, grads, losses = split(case)
+    res = ops.loss_fwd_bwd(to_dev(outs), to_dev(batch), case_args(case['meta']))
+    torch.cuda.synchronize()
+    got = dict(zip(ops.LOSS_KEYS, res.losses.cpu().tolist()))
+    for k, ref in losses.items():
+        assert abs(got[k] - ref) <= RTOL * abs(ref) + 1e-5, (name, scan, k, got[k], ref)
+    np.testing.assert_allclose(res.dpolicy.cpu().numpy(), grads['policy'], rtol=0, atol=ATOL)
+    if 'value' in grads:
+        np.testing.assert_allclose(res.dvalue.cpu().numpy(), grads['value'], rtol=0, atol=ATOL)
+    if 'return' in grads:
+        np.testing.assert_allclose(res.dreturn.cpu().numpy(), grads['return'], rtol=0, atol=ATOL)
