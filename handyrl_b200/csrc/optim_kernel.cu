@@ -80,6 +80,74 @@ __global__ void __launch_bounds__(kOptThreads) clip_adam_kernel(
     }
 }
 
+// ---- one-shot all-reduce over NVLink peer memory, fused with the sum-of-squares partials -------------------
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float *p) {   // never served from a stale cache line
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+constexpr int kMaxWorld = 16;
+
+__global__ void __launch_bounds__(kOptThreads) peer_allreduce_sumsq_kernel(
+    float *__restrict__ out, const float *const *__restrict__ peers, int64_t flag_offset, int world, int rank, int64_t n,
+    int64_t n_norm, float *__restrict__ partials, uint32_t *epoch_p, uint32_t *ticket_p) {
+    __shared__ const float *s_peer[kMaxWorld];
+    __shared__ uint32_t s_epoch;
+    if (threadIdx.x < world) s_peer[threadIdx.x] = peers[threadIdx.x];
+    __syncthreads();
+    uint32_t *my_flags = reinterpret_cast<uint32_t *>(const_cast<float *>(s_peer[rank])) + flag_offset;
+    if (threadIdx.x == 0) {
+        const uint32_t e = *epoch_p + 1;        // read by every block before the last block bumps it (ticket below)
+        s_epoch = e;
+        if (blockIdx.x == 0)                    // "my gradients are ready" -> slot [rank] of every rank's flags
+            for (int p = 0; p < world; p++)
+                st_release_sys(reinterpret_cast<uint32_t *>(const_cast<float *>(s_peer[p])) + flag_offset + rank, e);
+        for (int p = 0; p < world; p++)         // wait until every rank's gradients are ready (epochs only grow)
+            while (ld_acquire_sys(my_flags + p) < e) {}
+    }
+    __syncthreads();
+
+    float acc = 0.f;
+    const int64_t n4 = n >> 2;                  // n is a multiple of 4 (FlatAdam pads the bucket)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 s = ld_peer_f4(s_peer[0] + 4 * i);
+        for (int r = 1; r < world; r++) {       // fixed rank order: bit-identical sums on every rank
+            const float4 v = ld_peer_f4(s_peer[r] + 4 * i);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        reinterpret_cast<float4 *>(out)[i] = s;
+        if (4 * i < n_norm) acc += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
+    }
+    __shared__ float red[kOptThreads / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < kOptThreads / 32; w++) s += red[w];
+        partials[blockIdx.x] = s;
+        __threadfence();
+        if (atomicAdd(ticket_p, 1u) == gridDim.x - 1) {      // last block: every block of this rank has finished reading
+            const uint32_t e = s_epoch;
+            *ticket_p = 0u;
+            for (int p = 0; p < world; p++)                  // "I am done reading" -> slot [world + rank]
+                st_release_sys(reinterpret_cast<uint32_t *>(const_cast<float *>(s_peer[p])) + flag_offset + world + rank, e);
+            for (int p = 0; p < world; p++)                  // nobody still reads MY bucket -> the next step may overwrite it
+                while (ld_acquire_sys(my_flags + world + p) < e) {}
+            *epoch_p = e;
+        }
+    }
+}
+
 // the step counter is bumped by a 1-thread epilogue so that every block of clip_adam_kernel
 // reads the same value regardless of scheduling
 __global__ void bump_step_kernel(int64_t *step_p) { *step_p += 1; }
@@ -87,6 +155,21 @@ __global__ void bump_step_kernel(int64_t *step_p) { *step_p += 1; }
 }  // namespace hrl
 
 extern "C" int32_t hrl_sumsq_num_partials(void) { return hrl::kPartials; }
+
+extern "C" int hrl_peer_allreduce_sumsq(float *out_sum, const float *const *peer_buckets, int64_t flag_offset, int32_t world,
+                                        int32_t rank, int64_t n, int64_t n_norm, float *partials, uint32_t *epoch, uint32_t *ticket,
+                                        void *stream) {
+    using namespace hrl;
+    HRL_REQUIRE(out_sum && peer_buckets && partials && epoch && ticket, HRL_ERR_BAD_ARG, "hrl_peer_allreduce_sumsq: NULL pointer");
+    HRL_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, HRL_ERR_BAD_ARG,
+                "hrl_peer_allreduce_sumsq: bad world/rank (%d/%d)", world, rank);
+    HRL_REQUIRE(n > 0 && (n & 3) == 0 && (n_norm & 3) == 0 && n_norm <= n && flag_offset >= n, HRL_ERR_BAD_ARG, "hrl_peer_allreduce_sumsq: n must be a positive multiple of 4 and the flags must follow the data");
+    // the whole grid must be co-resident (blocks spin on peer flags): 296 blocks x 256 threads always are on B200
+    peer_allreduce_sumsq_kernel<<<kPartials, kOptThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        out_sum, peer_buckets, flag_offset, world, rank, n, n_norm, partials, epoch, ticket);
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
 
 extern "C" int hrl_grad_sumsq(const float *grad, int64_t n, float *partials, void *stream) {
     using namespace hrl;

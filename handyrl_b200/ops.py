@@ -170,7 +170,7 @@ class FlatAdam:
     all-reduce).
     """
 
-    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, max_norm=4.0, extra=0):
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, max_norm=4.0, extra=0, grad_alloc=None):
         params = [p for p in params]
         assert len(params) > 0 and all(p.is_cuda and p.dtype == torch.float32 for p in params)
         self.params = params
@@ -179,7 +179,12 @@ class FlatAdam:
         n_pad = (self.n + 3) // 4 * 4
         self.extra = extra
         self.flat_param = torch.zeros(n_pad, dtype=torch.float32, device=device)
-        self.flat_grad = torch.zeros(n_pad + extra, dtype=torch.float32, device=device)
+        extra = (extra + 3) // 4 * 4
+        self.extra = extra
+        # grad_alloc(numel) lets the caller place the bucket in NVLink-symmetric memory (peer all-reduce)
+        self.grad_storage = grad_alloc(n_pad + extra) if grad_alloc is not None else None
+        self.flat_grad = (self.grad_storage[:n_pad + extra] if self.grad_storage is not None
+                          else torch.zeros(n_pad + extra, dtype=torch.float32, device=device))
         off = 0
         with torch.no_grad():
             for p in params:
@@ -207,6 +212,14 @@ class FlatAdam:
     def zero_grad(self):
         self.flat_grad.zero_()
 
+    def step_reduced(self, reduced):
+        """clip + Adam on an already all-reduced bucket whose sum-of-squares partials are in self.partials
+        (hrl_peer_allreduce_sumsq)."""
+        check(lib().hrl_clip_adam_step(_ptr(self.flat_param), _ptr(reduced), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
+                                       self.n_pad, _ptr(self.partials), _ptr(self.lr), _ptr(self.step_count), self.max_norm,
+                                       self.betas[0], self.betas[1], self.eps, self.weight_decay, _ptr(self.grad_norm),
+                                       _stream_ptr()))
+
     def step(self):
         s = _stream_ptr()
         check(lib().hrl_grad_sumsq(_ptr(self.flat_grad), self.n_pad, _ptr(self.partials), s))
@@ -214,3 +227,46 @@ class FlatAdam:
                                        _ptr(self.exp_avg_sq), self.n_pad, _ptr(self.partials), _ptr(self.lr),
                                        _ptr(self.step_count), self.max_norm, self.betas[0], self.betas[1], self.eps,
                                        self.weight_decay, _ptr(self.grad_norm), s))
+
+
+class PeerAllReduce:
+    """One-shot all-reduce(SUM) of the flat gradient bucket over NVLink peer memory, fused with the gradient-norm
+    partials (hrl_peer_allreduce_sumsq).  The bucket lives in torch symmetric memory so that every rank holds a
+    mapping of every other rank's bucket; ranks synchronise inside the kernel with system-scope flags stored
+    behind the bucket.  Bit-identical results on all ranks (fixed summation order), CUDA-graph capturable,
+    no NCCL call on the step."""
+
+    def __init__(self, group, device):
+        import torch.distributed as dist
+        self.group, self.device = group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.numel = None
+
+    def alloc(self, numel):
+        """Bucket of `numel` floats (+ 2*world flag words) in symmetric memory; rendezvous with the peers."""
+        import torch.distributed._symmetric_memory as symm
+        self.numel = numel
+        words = numel + 2 * self.world + 64
+        self.storage = symm.empty(words, dtype=torch.float32, device=self.device)
+        self.storage.zero_()
+        try:
+            self.handle = symm.rendezvous(self.storage, self.group)
+        except Exception:
+            symm.enable_symm_mem_for_group(self.group.group_name)
+            self.handle = symm.rendezvous(self.storage, self.group.group_name)
+        torch.cuda.synchronize(self.device)
+        self.handle.barrier()
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        assert len(ptrs) == self.world and ptrs[self.rank] == self.storage.data_ptr()
+        self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        self.reduced = torch.zeros(numel, dtype=torch.float32, device=self.device)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return self.storage
+
+    def __call__(self, n_norm, partials):
+        """Enqueue the fused reduce on the current stream; returns the reduced bucket."""
+        check(lib().hrl_peer_allreduce_sumsq(_ptr(self.reduced), _ptr(self.peer_ptrs), self.numel, self.world, self.rank,
+                                             self.numel, n_norm, _ptr(partials), _ptr(self.epoch), _ptr(self.ticket),
+                                             _stream_ptr()))
+        return self.reduced

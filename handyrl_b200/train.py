@@ -14,6 +14,7 @@ Same public names as handyrl/train.py for the path
     (the reference does 4-6 .item() syncs per step, train.py:200, 375-376).
 """
 import copy
+import os
 import queue
 import random
 import threading
@@ -228,7 +229,7 @@ class LearnerStep:
 
     def __init__(self, model, args, example_batch, lr, device=None, process_group=None, use_graph=True,
                  max_norm=4.0, weight_decay=1e-5, time_loss_kernel=False, channels_last=True, cudnn_benchmark=True,
-                 small_boards=True):
+                 small_boards=True, peer_allreduce=None):
         self.device = torch.device(device if device is not None else 'cuda')
         self.args = args
         self.model = model.to(self.device)
@@ -249,7 +250,12 @@ class LearnerStep:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         params = [p for p in self.model.parameters()]
-        self.opt = ops.FlatAdam(params, lr=lr, weight_decay=weight_decay, max_norm=max_norm, extra=NUM_LOSS)
+        # gradient exchange: fused one-shot all-reduce over NVLink peer memory (default when sharded), or NCCL
+        if peer_allreduce is None:
+            peer_allreduce = self.world > 1 and os.environ.get('HRL_PEER_ALLREDUCE', '1') != '0'
+        self.peer = ops.PeerAllReduce(self.pg, self.device) if (peer_allreduce and self.world > 1) else None
+        self.opt = ops.FlatAdam(params, lr=lr, weight_decay=weight_decay, max_norm=max_norm, extra=NUM_LOSS,
+                                grad_alloc=self.peer.alloc if self.peer is not None else None)
 
         self.layout = BatchLayout(example_batch)
         self.dev_buffer = torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=self.device)
@@ -295,11 +301,16 @@ class LearnerStep:
             heads.append(outs['return'])
             grads.append(buf.dreturn)
         torch.autograd.backward(heads, grads)
-        self.opt.extra_slots.copy_(buf.losses)            # the loss sums ride the gradient bucket
-        if self.world > 1:
-            torch.distributed.all_reduce(self.opt.flat_grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
-        self.opt.step()
-        self.last_losses.copy_(self.opt.extra_slots)
+        self.opt.extra_slots[:NUM_LOSS].copy_(buf.losses)     # the loss sums ride the gradient bucket
+        if self.peer is not None:
+            reduced = self.peer(self.opt.n_pad, self.opt.partials)      # all-reduce + norm partials, one kernel
+            self.opt.step_reduced(reduced)
+            self.last_losses.copy_(reduced[self.opt.n_pad:self.opt.n_pad + NUM_LOSS])
+        else:
+            if self.world > 1:
+                torch.distributed.all_reduce(self.opt.flat_grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            self.opt.step()
+            self.last_losses.copy_(self.opt.extra_slots[:NUM_LOSS])
         self.loss_accum.add_(self.last_losses)
 
     def _device_step(self):

@@ -10,6 +10,8 @@
  *                            handyrl/losses.py:16-80  (monte_carlo / temporal_difference / upgo / vtrace)
  *                            + the autograd pass of train.py:369 restricted to those ops
  *   hrl_compute_target    <- handyrl/losses.py:63-80  (compute_target, stand-alone)
+ *   hrl_peer_allreduce_sumsq <- the gradient exchange nn.DataParallel does implicitly (train.py:339-340), as a
+ *                            fused peer-memory kernel
  *   hrl_grad_sumsq /
  *   hrl_clip_adam_step    <- handyrl/train.py:370-371 (clip_grad_norm_(params, 4.0) + Adam.step,
  *                            Adam(lr, weight_decay=1e-5) of train.py:331)
@@ -147,6 +149,24 @@ int hrl_clip_adam_step(float *param, const float *grad, float *exp_avg, float *e
                        int64_t n, const float *partials, const float *lr, int64_t *step,
                        double max_norm, double beta1, double beta2, double eps, double weight_decay,
                        float *grad_norm_out /* may be NULL */, void *stream);
+
+/*
+ * Multi-GPU form of the same step: one-shot all-reduce (SUM) of the flat gradient bucket over NVLink peer
+ * memory, fused with the sum-of-squares partials hrl_clip_adam_step consumes (replaces NCCL all-reduce +
+ * hrl_grad_sumsq).  Every rank reads every rank's bucket directly (P2P loads through NVSwitch), adds them in
+ * rank order -- all ranks get bit-identical sums -- and writes the result to `out_sum`.
+ *   peer_buckets  device array [world] of pointers: this process's mapping of rank r's bucket (index r);
+ *                 each bucket holds n floats followed by 2*world uint32 flags (zero-initialised once)
+ *   flag_offset   index (in 32-bit words from the bucket start) of the flags
+ *   n, n_norm     floats to reduce; the first n_norm of them (the gradients proper, not the loss sums riding in
+ *                 the tail) enter the sum of squares
+ *   epoch, ticket device uint32, zero-initialised once; maintained by the kernel (CUDA-graph safe)
+ * Ranks synchronise inside the kernel with release/acquire flags at system scope: "my gradients are ready"
+ * before the loads, "I am done reading" after them, so the next step may overwrite the bucket.
+ */
+int hrl_peer_allreduce_sumsq(float *out_sum, const float *const *peer_buckets, int64_t flag_offset, int32_t world,
+                             int32_t rank, int64_t n, int64_t n_norm, float *partials, uint32_t *epoch, uint32_t *ticket,
+                             void *stream);
 
 /*
  * Replay gather/pad: the device form of make_batch (train.py:33-124).
