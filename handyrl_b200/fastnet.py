@@ -32,6 +32,34 @@ def _selection(kh, kw, H, W, ph, pw, device, dtype):
     return S.to(device)
 
 
+class _SplitKLinear(torch.autograd.Function):
+    """y = x @ W^T with the weight gradient computed split-K: for N ~ 10^4 rows and a (C*HW)^2 weight the plain
+    wgrad GEMM (dy^T @ x, reduction over N) has only ~80 output tiles -- about half of B200's 148 SMs, each looping
+    over all N rows.  Splitting N into chunks turns it into a batched GEMM with chunks x 80 tiles plus a tiny sum."""
+
+    CHUNKS = int(__import__('os').environ.get('HRL_SPLITK', '32'))
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return x @ w.t()
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = dy @ w
+        if ctx.needs_input_grad[1]:
+            N = x.shape[0]
+            S = _SplitKLinear.CHUNKS
+            if N % S == 0 and N // S >= 256:
+                dw = torch.bmm(dy.reshape(S, N // S, -1).transpose(1, 2), x.reshape(S, N // S, -1)).sum(0)
+            else:
+                dw = dy.t() @ x
+        return dx, dw
+
+
 class BoardConv2d(nn.Conv2d):
     """nn.Conv2d whose forward runs as a dense GEMM when the board is tiny."""
 
@@ -59,7 +87,7 @@ class BoardConv2d(nn.Conv2d):
         # dense matrix of the layer: Wb[(o,q),(i,p)] = sum_k w[o,i,k] S[k,q,p]
         Wb = (self.weight.reshape(Cout * Cin, -1) @ S.reshape(S.shape[0], HW * HW))
         Wb = Wb.reshape(Cout, Cin, HW, HW).permute(0, 2, 1, 3).reshape(Cout * HW, Cin * HW)
-        y = F.linear(x.reshape(N, Cin * HW), Wb)
+        y = _SplitKLinear.apply(x.reshape(N, Cin * HW), Wb)
         y = y.reshape(N, Cout, H, W)
         if self.bias is not None:
             y = y + self.bias.view(1, Cout, 1, 1)
