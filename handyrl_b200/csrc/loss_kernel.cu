@@ -692,7 +692,7 @@ static int env_int(const char *name, int dflt) {
 }  // namespace hrl
 
 extern "C" size_t hrl_loss_workspace_bytes(int32_t B, int32_t, int32_t, int32_t, int32_t) {
-    return 2048 + 2 * (size_t)(B > 0 ? B : 0) * 8 * sizeof(float);   // header (ticket, per-SM arrivals) + up to two CTAs per window
+    return 2048 + 8 * (size_t)(B > 0 ? B : 0) * 8 * sizeof(float);   // header (ticket) + up to eight CTAs (a cluster) per window
 }
 
 extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
