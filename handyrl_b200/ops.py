@@ -11,7 +11,6 @@ import torch
 from . import _capi
 from ._capi import ALGO_ID, LOSS_KEYS, NUM_LOSS, HrlLossArgs, check, lib
 
-_workspaces = {}
 _BATCH_KEYS = ('action_mask', 'action', 'selected_prob', 'reward', 'return', 'turn_mask', 'observation_mask',
                'episode_mask', 'progress', 'outcome')
 
@@ -32,15 +31,6 @@ def _dev_f32(t, name):
 
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
-
-
-def _workspace(nbytes, device):
-    key = (device.index, torch.cuda.current_stream().cuda_stream)
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
-    return ws
 
 
 def algo_id(name):

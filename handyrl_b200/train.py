@@ -16,13 +16,11 @@ Same public names as handyrl/train.py for the path
 import copy
 import os
 import queue
-import random
 import threading
 import time
 from collections import deque
 
 import torch
-import torch.nn as nn
 
 from . import ops, fastnet
 from .batch import tree_map, tree_leaves, make_batch, flatten_moments, decode_moments, gather_windows, sample_window

@@ -178,3 +178,50 @@ def test_both_recurrence_forms_match_reference(name, scan, monkeypatch):
         np.testing.assert_allclose(res.dvalue.cpu().numpy(), grads['value'], rtol=0, atol=ATOL)
     if 'return' in grads:
         np.testing.assert_allclose(res.dreturn.cpu().numpy(), grads['return'], rtol=0, atol=ATOL)
+
+
+MODE_CASES = ['alt_UPGO_VTRACE', 'obs_TD_TD', 'geese4', 'wide', 'wide512', 'odd33', 'burnin_obs', 'novalue_ret', 'solo1']
+
+
+@pytest.mark.parametrize('mode', ['0', '1', '2', '3'], ids=['rows-direct', 'rows-staged', 'bulk', 'element'])
+@pytest.mark.parametrize('name', MODE_CASES)
+def test_every_kernel_variant_matches_reference(name, mode, monkeypatch):
+    """HRL_LOSS_MODE forces one data-movement variant of the fused kernel (falling back to the direct rows kernel
+    where a variant does not apply to the shape): all of them must reproduce the reference."""
+    from handyrl_b200 import ops
+    monkeypatch.setenv('HRL_LOSS_MODE', mode)
+    case = LOSS_CASES[name]
+    batch, outs, grads, losses = split(case)
+    res = ops.loss_fwd_bwd(to_dev(outs), to_dev(batch), case_args(case['meta']))
+    torch.cuda.synchronize()
+    got = dict(zip(ops.LOSS_KEYS, res.losses.cpu().tolist()))
+    for k, ref in losses.items():
+        assert abs(got[k] - ref) <= RTOL * abs(ref) + 1e-5, (name, mode, k, got[k], ref)
+    np.testing.assert_allclose(res.dpolicy.cpu().numpy(), grads['policy'], rtol=0, atol=ATOL)
+    if 'value' in grads:
+        np.testing.assert_allclose(res.dvalue.cpu().numpy(), grads['value'], rtol=0, atol=ATOL)
+    if 'return' in grads:
+        np.testing.assert_allclose(res.dreturn.cpu().numpy(), grads['return'], rtol=0, atol=ATOL)
+
+
+def test_wide_rows_without_staging_and_cluster_forms(monkeypatch):
+    """Full-size wide-row shape through the non-default forms: 1-CTA bulk, rows-direct with and without z staging."""
+    from handyrl_b200 import ops
+    from handyrl_b200.synthetic import synthetic_batch, synthetic_outputs
+    args = {'turn_based_training': True, 'observation': False, 'gamma': 0.8, 'lambda': 0.7, 'burn_in_steps': 0,
+            'entropy_regularization': 0.1, 'entropy_regularization_decay': 0.1, 'policy_target': 'UPGO', 'value_target': 'VTRACE'}
+    batch = synthetic_batch(64, 64, 2, 512, seed=3, with_obs=False)
+    outs = synthetic_outputs(batch, seed=4)
+    db, do = {k: v.cuda() for k, v in batch.items()}, {k: v.cuda() for k, v in outs.items()}
+    ref = ops.loss_fwd_bwd(do, db, args)            # default: 2-CTA cluster bulk kernel (checked against the oracle elsewhere)
+    torch.cuda.synchronize()
+    for env in ({'HRL_LOSS_CLUSTER': '1'}, {'HRL_LOSS_MODE': '0'}, {'HRL_LOSS_MODE': '0', 'HRL_LOSS_STAGE': '0'}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        res = ops.loss_fwd_bwd(do, db, args)
+        torch.cuda.synchronize()
+        for k in env:
+            monkeypatch.delenv(k)
+        np.testing.assert_allclose(res.losses.cpu().numpy(), ref.losses.cpu().numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(res.dpolicy.cpu().numpy(), ref.dpolicy.cpu().numpy(), rtol=0, atol=2e-6)
+        np.testing.assert_allclose(res.dvalue.cpu().numpy(), ref.dvalue.cpu().numpy(), rtol=0, atol=2e-6)
