@@ -181,6 +181,11 @@ def reference_arm(opt, w):
 
 # ------------------------------------------------------------------------------ B200 arm
 
+def loss_kernel_name(A):
+    """Which variant hrl_loss_fwd_bwd dispatches to for this action count (csrc/loss_kernel.cu)."""
+    return 'hrl::loss_elem_kernel' if A <= 32 else ('hrl::loss_bulk_kernel' if (A > 256 and A % 4 == 0) else 'hrl::loss_rows_kernel')
+
+
 def time_loss_alone(B, T, P, A, turn_based, observation, args, device, reps):
     """Average device time (ms) of hrl_loss_fwd_bwd launched back to back over input sets that together exceed L2."""
     from handyrl_b200 import ops
@@ -334,12 +339,13 @@ def b200_arm(opt, w):
                 'wall_s': wall_e2e, 'last_losses': last},
         'gpu_launches': 4 * opt.steps,          # loss fwd+bwd, grad sum-of-squares, clip+Adam, step counter
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': traffic, 'kernel': 'hrl::loss_elem_kernel (hrl_loss_fwd_bwd)', 'kernel_us': kernel_ms * 1e3,
+                     'traffic': traffic, 'kernel': loss_kernel_name(A) + ' (hrl_loss_fwd_bwd)', 'kernel_us': kernel_ms * 1e3,
                      'launches_timed': n_k, 'algorithmic_bytes': alg_bytes, 'peak_source': peak_src,
                      'alone_cold_us': None if alone is None else alone['ms'] * 1e3,
                      'alone_cold_gbs': None if alone is None else alg_bytes / (alone['ms'] * 1e-3) / 1e9,
-                     'note': 'event-bracketed single launch inside the step; 2.76 MB per launch is latency-bound '
-                             '(0.42 us at peak), see DESIGN.md section 4'},
+                     'note': 'event-bracketed single launch inside the step; %.2f MB per launch = %.2f us at peak%s, see '
+                             'DESIGN.md section 4' % (alg_bytes / 1e6, alg_bytes / peak / 1e3,
+                                                      ' (latency-bound: below one DRAM round trip + launch)' if alg_bytes < 2e7 else '')},
         'wall_s': wall,
     }
     if wide is not None:
@@ -347,7 +353,7 @@ def b200_arm(opt, w):
         line['roofline_wide_rows'] = {
             'workload': WORKLOADS['cfg5shard']['desc'] + ' (loss kernel alone, %d cold input sets)' % wide['sets'],
             'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
-            'kernel': 'hrl::loss_bulk_kernel (hrl_loss_fwd_bwd)', 'kernel_us': wide['ms'] * 1e3,
+            'kernel': loss_kernel_name(WORKLOADS['cfg5shard']['A']) + ' (hrl_loss_fwd_bwd)', 'kernel_us': wide['ms'] * 1e3,
             'algorithmic_bytes': wide['bytes'], 'traffic': None if traffic_all is None else traffic_all.get('cfg5shard')}
     if world == 1 and not opt.no_cpu:
         r = run_cpu_port(w, steps=8, warmup=1, budget_s=25.0)
