@@ -314,6 +314,8 @@ def b200_arm(opt, w):
         shutdown(stepper, world)
         return
 
+    from handyrl_b200 import fastnet
+    n_fused_bn = sum(isinstance(m, fastnet.BoardBatchNorm2d) for m in stepper.model.modules()) if w['net'] == 'tictactoe' else 0
     peak, peak_src = measured_peak()
     Pa = example['action_mask'].shape[2]
     alg_bytes = bytes_per_cell(P, Pa, A, T, 0) * B * T
@@ -337,7 +339,9 @@ def b200_arm(opt, w):
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e / opt.steps,
                 'h2d_bytes_per_step': nbytes * world, 'd2h_bytes_per_step': 24 * world,
                 'wall_s': wall_e2e, 'last_losses': last},
-        'gpu_launches': 4 * opt.steps,          # loss fwd+bwd, grad sum-of-squares, clip+Adam, step counter
+        # our kernels per step: loss fwd+bwd, [peer all-reduce+]grad sum-of-squares, clip+Adam, step counter,
+        # and 3 forward + 3 backward launches per fused BatchNorm layer of the (rewritten) net
+        'gpu_launches': (4 + 6 * n_fused_bn) * opt.steps,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'kernel': loss_kernel_name(A) + ' (hrl_loss_fwd_bwd)', 'kernel_us': kernel_ms * 1e3,
                      'launches_timed': n_k, 'algorithmic_bytes': alg_bytes, 'peak_source': peak_src,

@@ -102,10 +102,16 @@ class BoardBatchNorm2d(nn.BatchNorm2d):
         if not (self.training and x.dim() == 4 and x.shape[2] * x.shape[3] <= MAX_CELLS and self.track_running_stats):
             return super().forward(x)
         N, C, H, W = x.shape
-        x3 = x.reshape(N, C, H * W)
-        var, mean = torch.var_mean(x3, dim=(0, 2), unbiased=False, keepdim=True)
         if self.momentum is None:
             raise NotImplementedError('cumulative moving average BatchNorm is not rewritten')
+        if x.is_cuda and x.dtype == torch.float32 and self.affine:
+            # fused kernels (csrc/bn_kernel.cu): 3 coalesced passes forward, 3 backward
+            from . import ops
+            with torch.no_grad():
+                self.num_batches_tracked.add_(1)
+            return ops.batch_norm_train(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum)
+        x3 = x.reshape(N, C, H * W)
+        var, mean = torch.var_mean(x3, dim=(0, 2), unbiased=False, keepdim=True)
         with torch.no_grad():
             n = N * H * W
             self.num_batches_tracked.add_(1)

@@ -219,6 +219,41 @@ class FlatAdam:
                                        self.weight_decay, _ptr(self.grad_norm), s))
 
 
+class _BatchNormTrain(torch.autograd.Function):
+    """nn.BatchNorm2d (training mode) on (N, C, H, W) with a small board, through hrl_bn_train_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum):
+        x = x.contiguous()
+        N, Cn, H, W = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(Cn, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        ws = torch.empty(lib().hrl_bn_workspace_floats(N, Cn, H * W), dtype=torch.float32, device=x.device)
+        check(lib().hrl_bn_train_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(running_mean),
+                                     _ptr(running_var), N, Cn, H * W, float(eps), float(momentum), _ptr(ws), _stream_ptr()))
+        ctx.save_for_backward(x, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        N, Cn, H, W = x.shape
+        dx = torch.empty_like(x)
+        dgamma = torch.empty(Cn, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty_like(dgamma)
+        ws = torch.empty(lib().hrl_bn_workspace_floats(N, Cn, H * W), dtype=torch.float32, device=x.device)
+        check(lib().hrl_bn_train_bwd(_ptr(x), _ptr(dy), _ptr(weight), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                                     N, Cn, H * W, _ptr(ws), _stream_ptr()))
+        return dx, (dgamma if weight is not None else None), (dbeta if ctx.needs_input_grad[2] else None), None, None, None, None
+
+
+def batch_norm_train(x, weight, bias, running_mean, running_var, eps, momentum):
+    """Fused train-mode BatchNorm for small boards (updates the running statistics in place)."""
+    return _BatchNormTrain.apply(x, weight, bias, running_mean, running_var, eps, momentum)
+
+
 class PeerAllReduce:
     """One-shot all-reduce(SUM) of the flat gradient bucket over NVLink peer memory, fused with the gradient-norm
     partials (hrl_peer_allreduce_sumsq).  The bucket lives in torch symmetric memory so that every rank holds a

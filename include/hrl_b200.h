@@ -169,6 +169,20 @@ int hrl_peer_allreduce_sumsq(float *out_sum, const float *const *peer_buckets, i
                              void *stream);
 
 /*
+ * Train-mode BatchNorm over (N, C, HW) fp32 activations with small HW -- used by the small-board rewrite of the user's
+ * net (the nets of reference envs normalise (N,32,3,3) / (N,C,6,6) tensors; cuDNN / ATen launch one CTA per channel
+ * there).  Semantics of nn.BatchNorm2d in training mode: biased variance for the normalisation, unbiased for
+ * running_var, running stats updated with `momentum` (pass NULL for both to skip).  mean / rstd (C floats each) are
+ * saved for the backward.  workspace: hrl_bn_workspace_floats(N, C, HW) floats.
+ */
+size_t hrl_bn_workspace_floats(int64_t N, int32_t C, int32_t HW);
+int hrl_bn_train_fwd(const float *x, const float *gamma, const float *beta, float *y, float *mean, float *rstd,
+                     float *running_mean, float *running_var, int64_t N, int32_t C, int32_t HW, float eps, float momentum,
+                     float *workspace, void *stream);
+int hrl_bn_train_bwd(const float *x, const float *dy, const float *gamma, const float *mean, const float *rstd, float *dx,
+                     float *dgamma, float *dbeta, int64_t N, int32_t C, int32_t HW, float *workspace, void *stream);
+
+/*
  * Replay gather/pad: the device form of make_batch (train.py:33-124).
  *
  * Episodes are kept decoded in flat device arrays ("replay store"), one row per step:

@@ -79,3 +79,35 @@ def test_peer_allreduce_kernel_world1_matches_sumsq():
         assert int(epoch) == it + 1 and int(ticket) == 0
         want = float((bucket[:n_norm].double() ** 2).sum())
         assert abs(float(partials.double().sum()) - want) <= 1e-5 * want
+
+
+@pytest.mark.parametrize('shape', [(16384, 32, 3, 3), (1000, 8, 6, 6), (37, 5, 4, 5)])
+def test_fused_batchnorm_matches_torch(shape):
+    """hrl_bn_train_fwd / _bwd vs nn.BatchNorm2d in training mode: output, input/affine gradients, running statistics."""
+    from handyrl_b200 import fastnet
+    torch.manual_seed(0)
+    N, C, H, W = shape
+    ref = torch.nn.BatchNorm2d(C).cuda().train()
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5)
+        ref.bias.uniform_(-0.5, 0.5)
+    import copy
+    fast = torch.nn.Sequential(copy.deepcopy(ref))
+    assert fastnet.optimize_small_boards(fast) == 1
+    old = torch.backends.cudnn.enabled
+    for it in range(2):
+        x = (torch.randn(shape, device='cuda') * 2 + 0.5)
+        xr, xf = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        g = torch.randn(shape, device='cuda')
+        yr = ref(xr)
+        yf = fast(xf)
+        yr.backward(g)
+        yf.backward(g)
+        torch.testing.assert_close(yf, yr, rtol=1e-5, atol=2e-5)
+        torch.testing.assert_close(xf.grad, xr.grad, rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(fast[0].weight.grad, ref.weight.grad, rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(fast[0].bias.grad, ref.bias.grad, rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(fast[0].running_mean, ref.running_mean, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(fast[0].running_var, ref.running_var, rtol=1e-5, atol=1e-6)
+        assert int(fast[0].num_batches_tracked) == int(ref.num_batches_tracked) == it + 1
+    torch.backends.cudnn.enabled = old
