@@ -98,3 +98,58 @@ def test_trainer_thread_protocol(gpu_replay):
     tr.stop()
     th.join(timeout=10)
     assert not th.is_alive()
+
+
+@pytest.mark.parametrize('name', sorted(RNN_CASES))
+def test_recurrent_learner_step_graph_equals_eager_and_reference_losses(name):
+    """The recurrent path (hidden masking, burn-in in eval mode, dict observations) inside LearnerStep: the first
+    step's loss sums match the reference's, and the CUDA-graph step is identical to the eager one over 3 steps."""
+    from handyrl_b200.batch import tree_map
+    from handyrl_b200.nets import GatedBoardNet
+    from handyrl_b200.train import LearnerStep
+    c = RNN_CASES[name]
+    batch = tree_map(lambda a: torch.from_numpy(a), c['batch'])
+    results = {}
+    for use_graph in (False, True):
+        net = GatedBoardNet()
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in c['state0'].items()})
+        stepper = LearnerStep(net, c['args'], batch, lr=1e-3, use_graph=use_graph)
+        losses = []
+        for _ in range(3):
+            stepper.step(stepper.new_packed().fill(batch))
+            losses.append(stepper.read_losses())
+        results[use_graph] = (losses, stepper.cpu_state_dict())
+    first = results[True][0][0]
+    for k, v in c['losses'].items():
+        assert abs(first[k] - v) <= 1e-4 * abs(v) + 1e-4, (k, first[k], v)
+    assert first['dcnt'] == c['dcnt']
+    for a, b in zip(results[False][0], results[True][0]):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-5 * abs(a[k]) + 1e-5, (k, a[k], b[k])
+    for (k, va), (_, vb) in zip(results[False][1].items(), results[True][1].items()):
+        torch.testing.assert_close(vb.float(), va.float(), rtol=1e-4, atol=1e-5, msg=k)
+
+
+def test_trainer_on_geister_episodes_with_gpu_replay():
+    """Dict observations + burn-in + recurrent net + GPU-resident replay through the Trainer thread protocol."""
+    import threading
+    from handyrl_b200.train import Trainer
+    from handyrl_b200.nets import GatedBoardNet
+    with open(os.path.join(GOLDEN, 'batch_cases.pkl'), 'rb') as f:
+        case = pickle.load(f)['geister_burnin']
+    args = dict(case['args'], batch_size=6, minimum_episodes=4, num_batchers=1, **{'lambda': 0.7},
+                entropy_regularization=0.1, entropy_regularization_decay=0.1, policy_target='TD', value_target='TD',
+                gpu_replay=True)
+    net = GatedBoardNet(scalars=18, planes=7, board=(6, 6), width=8, actions=214)
+    tr = Trainer(args, net)
+    tr.episodes.extend(case['episodes'])
+    th = threading.Thread(target=tr.run, daemon=True)
+    th.start()
+    model, steps = tr.update()
+    assert steps >= 1 and not model.training
+    assert all(torch.isfinite(p).all() for p in model.parameters())
+    model2, steps2 = tr.update()
+    assert steps2 > steps
+    tr.stop()
+    th.join(timeout=10)
+    assert not th.is_alive()
