@@ -38,13 +38,19 @@ WORKLOADS = {
     'cfg5shard': dict(B=512, T=64, P=2, A=512, turn_based=True, observation=False, obs_shape=(1, 64, 64), net='wide',
                       policy_target='UPGO', value_target='VTRACE', reward_kind='zero',
                       desc='configs[4] per-GPU shard: 64x64 obs / 512 actions, T=64 B=512/GPU P=2 Pa=1'),
+    # BASELINE.json configs[2]: Geister-shaped recurrent net (dict observation, policy/value/return heads), TD(lambda),
+    # batch 256, burn-in 4 + 16 forward steps
+    'cfg3': dict(B=256, T=20, P=2, A=214, turn_based=True, observation=True, obs_shape=None, net='geister', burn_in=4,
+                 policy_target='TD', value_target='TD', reward_kind='step',
+                 desc='configs[2]: Geister-shaped recurrent net (conv-gated memory, 3 heads), TD(lambda), B=256/GPU, '
+                      'T=4 burn-in + 16, P=Pa=2, A=214, dict observation {scalar 18, board 7x6x6}'),
 }
 L2_BYTES = 126e6
 
 
 def train_args(w):
     return {'turn_based_training': w['turn_based'], 'observation': w['observation'], 'gamma': 0.8, 'lambda': 0.7,
-            'burn_in_steps': 0, 'forward_steps': w['T'], 'entropy_regularization': 0.1,
+            'burn_in_steps': w.get('burn_in', 0), 'forward_steps': w['T'] - w.get('burn_in', 0), 'entropy_regularization': 0.1,
             'entropy_regularization_decay': 0.1, 'policy_target': w['policy_target'], 'value_target': w['value_target'],
             'batch_size': w['B']}
 
@@ -52,11 +58,21 @@ def train_args(w):
 def make_net(w):
     from handyrl_b200 import nets
     torch.manual_seed(0)
+    if w['net'] == 'geister':
+        return nets.GatedBoardNet(scalars=18, planes=7, board=(6, 6), width=32, actions=w['A'])
     return nets.tictactoe_net() if w['net'] == 'tictactoe' else nets.WideActionNet()
 
 
 def make_batch(w, seed, B=None):
     from handyrl_b200.synthetic import synthetic_batch
+    if w['net'] == 'geister':
+        b = synthetic_batch(B or w['B'], w['T'], w['P'], w['A'], turn_based=w['turn_based'], observation=w['observation'],
+                            reward_kind=w['reward_kind'], seed=seed, burn_in=w.get('burn_in', 0), with_obs=False)
+        g = torch.Generator().manual_seed(seed + 7)
+        Bn, T, Pa = b['action'].shape[:3]
+        b['observation'] = {'scalar': torch.rand((Bn, T, Pa, 18), generator=g),
+                            'board': (torch.rand((Bn, T, Pa, 7, 6, 6), generator=g) < 0.3).float()}
+        return b
     return synthetic_batch(B or w['B'], w['T'], w['P'], w['A'], turn_based=w['turn_based'], observation=w['observation'],
                            reward_kind=w['reward_kind'], seed=seed, obs_shape=w['obs_shape'])
 
@@ -165,6 +181,9 @@ def reference_arm(opt, w):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return      # the host has one set of cores: rank 0 alone measures it
+    if w['net'] == 'geister':
+        print(json.dumps({'impl': 'reference', 'unavailable': 'the CPU port (oracle/torch_learner.py) covers feed-forward nets only'}), flush=True)
+        return
     r = run_cpu_port(w, opt.steps, opt.warmup, budget_s=150.0)
     sample = '%d steps of a B=%d x T=%d batch (workload B=%d)' % (opt.steps, r['B_sample'], w['T'], w['B'])
     line = {
@@ -318,7 +337,7 @@ def b200_arm(opt, w):
     n_fused_bn = sum(isinstance(m, fastnet.BoardBatchNorm2d) for m in stepper.model.modules()) if w['net'] == 'tictactoe' else 0
     peak, peak_src = measured_peak()
     Pa = example['action_mask'].shape[2]
-    alg_bytes = bytes_per_cell(P, Pa, A, T, 0) * B * T
+    alg_bytes = bytes_per_cell(P, Pa, A, T, 1 if w['net'] == 'geister' else 0) * B * T
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     traffic, traffic_all = None, None
     try:
@@ -359,7 +378,7 @@ def b200_arm(opt, w):
             'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
             'kernel': loss_kernel_name(WORKLOADS['cfg5shard']['A']) + ' (hrl_loss_fwd_bwd)', 'kernel_us': wide['ms'] * 1e3,
             'algorithmic_bytes': wide['bytes'], 'traffic': None if traffic_all is None else traffic_all.get('cfg5shard')}
-    if world == 1 and not opt.no_cpu:
+    if world == 1 and not opt.no_cpu and w['net'] != 'geister':     # the CPU port is feed-forward only
         r = run_cpu_port(w, steps=8, warmup=1, budget_s=25.0)
         r1 = run_cpu_port(w, steps=4, warmup=1, budget_s=12.0, threads=1)
         line['cpu_baseline'] = {
