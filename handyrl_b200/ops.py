@@ -81,7 +81,9 @@ def loss_fwd_bwd(outputs, batch, args, buffers=None, taps=False):
 
     # static buffers (CUDA-graph replays): the argument block of the previous call is still valid
     key = (policy.data_ptr(), 0 if value is None else value.data_ptr(), 0 if ret_head is None else ret_head.data_ptr(),
-           id(args)) + tuple(batch[k].data_ptr() for k in _BATCH_KEYS)
+           args['value_target'], args['policy_target'], bool(args['turn_based_training']), args.get('burn_in_steps', 0),
+           args['lambda'], args['gamma'], args['entropy_regularization'], args['entropy_regularization_decay'],
+           buffers.taps is not None) + tuple(batch[k].data_ptr() for k in _BATCH_KEYS)
     cached = getattr(buffers, '_cached', None)
     if cached is not None and cached[0] == key:
         check(lib().hrl_loss_fwd_bwd(C.byref(cached[1]), _stream_ptr()))
