@@ -712,7 +712,7 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     HRL_REQUIRE(a.dpolicy_raw && a.losses, HRL_ERR_BAD_ARG, "hrl_loss_fwd_bwd: a required output pointer is NULL");
     HRL_REQUIRE((a.value_raw != nullptr) == (a.dvalue_raw != nullptr) && (a.return_raw != nullptr) == (a.dreturn_raw != nullptr),
                 HRL_ERR_BAD_ARG, "hrl_loss_fwd_bwd: each head needs both its output and its gradient buffer");
-    HRL_REQUIRE(a.A <= 512, HRL_ERR_UNSUPPORTED, "hrl_loss_fwd_bwd: A=%d > 512 not built", a.A);
+    HRL_REQUIRE(a.A <= 1024, HRL_ERR_UNSUPPORTED, "hrl_loss_fwd_bwd: A=%d > 1024 not built", a.A);
     HRL_REQUIRE(a.P <= 64, HRL_ERR_UNSUPPORTED, "hrl_loss_fwd_bwd: P=%d > 64 not built", a.P);
 
     LossParams prm;
@@ -734,14 +734,14 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     // row mapping: one thread per row while the row fits in 16 registers, then 2..32 lanes per row
     int LPR = 1;
     while (LPR < 32 && (a.A + LPR - 1) / LPR > 16) LPR <<= 1;
-    const int NPL = LPR == 1 ? pow2_ceil(a.A) : 16;
+    const int NPL = LPR == 1 ? pow2_ceil(a.A) : (a.A > 512 ? 32 : 16);
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.policy_raw) & 15) == 0) &&
                            ((reinterpret_cast<uintptr_t>(a.action_mask) & 15) == 0) &&
                            ((reinterpret_cast<uintptr_t>(a.dpolicy_raw) & 15) == 0);
     const int mode = env_int("HRL_LOSS_MODE", -1);   // -1 auto, 0 direct, 1 staged I/O, 2 bulk
 
     // ---- bulk (TMA) kernel: wide rows
-    if (LPR == 32 && a.A % 4 == 0 && aligned16 && (mode == -1 || mode == 2)) {
+    if (LPR == 32 && a.A <= 512 && a.A % 4 == 0 && aligned16 && (mode == -1 || mode == 2)) {
         const size_t two_per_sm = 112 * 1024;     // dynamic shared memory that still lets two CTAs share an SM
         const int force_cs = env_int("HRL_LOSS_CLUSTER", 0);
         int NCmax = env_int("HRL_LOSS_CONSUMERS", 16);
@@ -854,6 +854,7 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     HRL_CASE2(1, 1) HRL_CASE2(1, 2) HRL_CASE2(1, 4) HRL_CASE2(1, 8) HRL_CASE2(1, 16)
     HRL_CASE2(2, 16) HRL_CASE2(4, 16) HRL_CASE2(8, 16) HRL_CASE2(16, 16) HRL_CASE2(32, 16)
     HRL_CASE(32, 16, true, false)
+    HRL_CASE2(32, 32) HRL_CASE(32, 32, true, false)      // 512 < A <= 1024
 #undef HRL_CASE2
 #undef HRL_CASE
     set_error("hrl_loss_fwd_bwd: no kernel for LPR=%d NPL=%d", LPR, NPL);

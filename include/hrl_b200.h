@@ -60,8 +60,8 @@ enum { HRL_LOSS_P = 0, HRL_LOSS_V = 1, HRL_LOSS_R = 2, HRL_LOSS_ENT = 3, HRL_LOS
  *
  * Dimensions: B windows, T = burn_in + forward steps, P players on the value side,
  * Pa players on the policy side (1 for the turn-alternating layout, else P; train.py:65-68),
- * A actions.  Steps t < burn_in are excluded from every loss term and receive zero
- * gradients (train.py:220-222).
+ * A actions (A <= 1024 and P <= 64 are built; larger values return HRL_ERR_UNSUPPORTED).  Steps t < burn_in are
+ * excluded from every loss term and receive zero gradients (train.py:220-222).
  */
 typedef struct HrlLossArgs {
     int32_t B, T, P, Pa, A;

@@ -225,3 +225,31 @@ def test_wide_rows_without_staging_and_cluster_forms(monkeypatch):
         np.testing.assert_allclose(res.losses.cpu().numpy(), ref.losses.cpu().numpy(), rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(res.dpolicy.cpu().numpy(), ref.dpolicy.cpu().numpy(), rtol=0, atol=2e-6)
         np.testing.assert_allclose(res.dvalue.cpu().numpy(), ref.dvalue.cpu().numpy(), rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize('A', [640, 1000, 1024])
+def test_action_spaces_up_to_1024_against_oracle(A):
+    from handyrl_b200 import ops
+    from handyrl_b200.synthetic import synthetic_batch, synthetic_outputs
+    from oracle import oracle
+    args = {'turn_based_training': True, 'observation': False, 'gamma': 0.8, 'lambda': 0.7, 'burn_in_steps': 0,
+            'entropy_regularization': 0.1, 'entropy_regularization_decay': 0.1, 'policy_target': 'UPGO', 'value_target': 'VTRACE'}
+    batch = synthetic_batch(6, 10, 2, A, seed=A, with_obs=False)
+    outs = synthetic_outputs(batch, seed=A + 1)
+    res = ops.loss_fwd_bwd({k: v.cuda() for k, v in outs.items()}, {k: v.cuda() for k, v in batch.items()}, args)
+    torch.cuda.synchronize()
+    orc = oracle.loss({k: v.numpy() for k, v in batch.items()}, {k: v.numpy() for k, v in outs.items()}, args, dtype=np.float64)
+    np.testing.assert_allclose(res.losses.cpu().numpy(), orc['losses'], rtol=RTOL, atol=1e-5)
+    np.testing.assert_allclose(res.dpolicy.cpu().numpy(), orc['dpolicy_raw'], rtol=0, atol=ATOL)
+    np.testing.assert_allclose(res.dvalue.cpu().numpy(), orc['dvalue_raw'], rtol=0, atol=ATOL)
+
+
+def test_action_space_beyond_the_built_range_is_refused():
+    from handyrl_b200 import ops, _capi
+    from handyrl_b200.synthetic import synthetic_batch, synthetic_outputs
+    args = {'turn_based_training': True, 'observation': False, 'gamma': 0.8, 'lambda': 0.7, 'burn_in_steps': 0,
+            'entropy_regularization': 0.1, 'entropy_regularization_decay': 0.1, 'policy_target': 'TD', 'value_target': 'TD'}
+    batch = synthetic_batch(2, 4, 2, 1500, seed=1, with_obs=False)
+    outs = synthetic_outputs(batch, seed=2)
+    with pytest.raises(_capi.HrlError, match='not built'):
+        ops.loss_fwd_bwd({k: v.cuda() for k, v in outs.items()}, {k: v.cuda() for k, v in batch.items()}, args)
