@@ -827,7 +827,9 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     // staged I/O when both the logits and the masks of the CTA's episodes fit comfortably (>= 2 CTAs per SM)
     prm.row_stride = (LPR == 1 && a.A % 2 == 0) ? a.A + 1 : a.A;
     const size_t io_floats = (size_t)EPB * R * prm.row_stride;
-    bool ios = !vec && (mode == -1 || mode == 1);
+    // staging through cp.async pays for narrow rows; from 16 lanes per row on (A > 128) direct coalesced loads and
+    // stores are faster (Geister shape, A=214: 35 us direct vs 41 us staged)
+    bool ios = !vec && ((mode == -1 && LPR < 16) || mode == 1);
     prm.stage_z = env_int("HRL_LOSS_STAGE", 1);
     SmemLayout L = make_layout(EPB, prm.Tt, a.P, a.Pa, 1, prm.row_stride, (int)io_floats, -1, false, prm.scan + 1);
     if (ios && (size_t)L.total * 4 > (mode == 1 ? smem_cap : (size_t)100 * 1024)) ios = false;
