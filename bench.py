@@ -202,7 +202,7 @@ def reference_arm(opt, w):
 
 def loss_kernel_name(A):
     """Which variant hrl_loss_fwd_bwd dispatches to for this action count (csrc/loss_kernel.cu)."""
-    return 'hrl::loss_elem_kernel' if A <= 32 else ('hrl::loss_bulk_kernel' if (A > 256 and A % 4 == 0) else 'hrl::loss_rows_kernel')
+    return 'hrl::loss_group_kernel' if A <= 32 else ('hrl::loss_bulk_kernel' if (A > 256 and A % 4 == 0) else 'hrl::loss_rows_kernel')
 
 
 def time_loss_alone(B, T, P, A, turn_based, observation, args, device, reps):

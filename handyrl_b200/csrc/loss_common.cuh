@@ -28,7 +28,7 @@ struct SmemLayout {
     int outcome;                                            // [EPB*P]
     int logp, rho, ent, mx, lsum, scale, vraw, rraw, prob;  // [rows]
     int act;                                                // [rows] int64 (2 floats each)
-    int red;                                                // [8*32]
+    int red;                                                // [12*32]
     int bars;                                               // mbarriers of the bulk loads, 8-byte aligned
     int z;                                                  // [rows*row_stride] if staged
     int am;                                                 // staged action mask: [rows*row_stride] or ring
@@ -73,7 +73,7 @@ __host__ __device__ inline SmemLayout make_layout(int EPB, int Tt, int P, int Pa
     o = (o + 1) & ~1;
     L.act = o; o += 2 * rows;
     o = (o + 3) & ~3;
-    L.red = o; o += 8 * 32;
+    L.red = o; o += 12 * 32;    // 6 x 32 floats for the block reduce, reused as 6 x 32 doubles by the final fold
     L.bars = o; o += 2 * (kMaxChunks + 2 * kMaxStages);
     o = (o + 31) & ~31;   // 128-byte alignment for the bulk-copy destinations
     L.z = o;
@@ -495,19 +495,19 @@ __device__ __forceinline__ void finalize_losses(const LossParams &prm, const Sme
 #pragma unroll
         for (int i = 0; i < 6; i++) acc[i] += (double)__ldcg(partials + (size_t)blk * 8 + i);
     }
-    double *dred = reinterpret_cast<double *>(smem + L.red);  // 8*32 floats = 128 doubles >= 6*20
+    double *dred = reinterpret_cast<double *>(smem + L.red);  // 12*32 floats = 192 doubles = 6 x 32 warps
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 6; i++) {
         double v = warp_sum_d(acc[i]);
-        if (wl == 0) dred[i * 20 + warp] = v;
+        if (wl == 0) dred[i * 32 + warp] = v;
     }
     __syncthreads();
     if (c.tid == 0) {
         double s[6];
         for (int i = 0; i < 6; i++) {
             s[i] = 0;
-            for (int w2 = 0; w2 < nwarp; w2++) s[i] += dred[i * 20 + w2];
+            for (int w2 = 0; w2 < nwarp; w2++) s[i] += dred[i * 32 + w2];
         }
         const double lv = 0.5 * s[1];
         float *out = prm.a.losses;

@@ -445,6 +445,94 @@ __global__ void __launch_bounds__(1024) loss_elem_kernel(const LossParams prm) {
     HRL_STAMP(6);
 }
 
+// ======================================================================== group kernel (small action spaces, fewer stages)
+// Same job as the element kernel with fewer barrier-separated stages: RL = 2^k >= A lanes own one row, so the row
+// maximum, the exponential sums and the gathered logit are warp shuffles inside the lane group (one fused stage
+// instead of four), and the gradient stage recomputes the row factors per lane instead of a separate row pass.
+template <int RL>
+__global__ void __launch_bounds__(1024) loss_group_kernel(const LossParams prm) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ bool s_last;
+    const HrlLossArgs &a = prm.a;
+    const CtaCtx c = make_ctx(prm);
+    const int P = c.P, Pa = c.Pa, A = c.A, Tt = c.Tt, T0 = c.T0, bi = c.bi, tid = c.tid, nthr = c.nthr;
+    const int R = Tt * Pa;
+    const SmemLayout L = make_layout(prm.EPB, Tt, P, Pa, 1, A, 0, -1, false, prm.scan + 1);
+    const long long *s_act = reinterpret_cast<const long long *>(smem + L.act);
+    float *s_z = smem + L.z;
+    const int grp = tid / RL, lane = tid % RL, ngrp = nthr / RL;
+    HRL_STAMP(0);
+
+    stage_small(prm, L, smem, c);
+
+    // ---- stage 1: masked logits + row statistics, one lane per element, reductions by shuffles
+    for (int base = 0; base < c.nrows; base += ngrp) {
+        const int r = base + grp;
+        const bool valid = r < c.nrows, live = valid && lane < A;
+        float z = -INFINITY, scale = 0.0f;
+        int act = 0;
+        if (valid) {
+            const int e = (c.nE == 1) ? 0 : r / R, rr = r - e * R, t = fdiv(rr, Pa, c.shPa), q = rr - t * Pa;
+            const size_t cell = (size_t)(c.b0 + e) * T0 + bi + t;
+            if (Pa == P) scale = a.turn_mask[cell * P + q];
+            else for (int p = 0; p < P; p++) scale += a.turn_mask[cell * P + p];   // train.py:179-180
+            act = (int)a.action[cell * Pa + q];
+            if (live) {
+                const size_t g = (cell * Pa + q) * A + lane;
+                z = ld_stream(a.policy_raw + g) * scale - ld_stream(a.action_mask + g);   // train.py:178-181
+                s_z[r * A + lane] = z;
+            }
+        }
+        const float m = group_max<RL>(z);
+        const float za = group_max<RL>((live && lane == act) ? z : -INFINITY);
+        const float d = live ? z - m : 0.0f;
+        const float ex = live ? expf(d) : 0.0f;
+        const float se = group_sum<RL>(ex);
+        const float sw = group_sum<RL>(ex * fmaxf(d, -3.0e38f));
+        if (valid && lane == 0) store_row_stats(L, smem, r, za, m, se, sw, scale);
+    }
+    cp_async_wait_all();
+    HRL_STAMP(1);
+    __syncthreads();
+    baselines(prm, L, smem, c);
+    row_epilogue(prm, L, smem, c);
+    HRL_STAMP(2);
+    __syncthreads();
+    HRL_STAMP(3);
+
+    float part[6];
+    targets_and_losses(prm, L, smem, c, part);
+    HRL_STAMP(4);
+    reduce_partials(L, smem, c, part);
+    if ((tid >> 5) == (nthr >> 5) - 1) publish_partials(prm, L, smem, c, &s_last);
+    HRL_STAMP(5);
+
+    // ---- stage 3: gradients; every lane gathers its row's factors itself (no separate row pass)
+    for (int base = 0; base < c.nrows; base += ngrp) {
+        const int r = base + grp;
+        if (r >= c.nrows) continue;
+        const int e = (c.nE == 1) ? 0 : r / R, rr = r - e * R, t = fdiv(rr, Pa, c.shPa), q = rr - t * Pa;
+        const RowFactors f = row_factors(prm, L, smem, e * Tt + t, q, P, Pa);
+        const size_t grow = ((size_t)(c.b0 + e) * T0 + bi) * Pa + rr;
+        if (lane < A) {
+            const float scale = smem[L.scale + r];
+            float g = 0.0f;
+            if (scale != 0.0f)
+                g = grad_elem(s_z[r * A + lane], lane == (int)s_act[r], smem[L.mx + r], smem[L.lsum + r], smem[L.ent + r], f.w, f.k, scale);
+            st_stream(a.dpolicy_raw + grow * A + lane, g);
+        }
+        if (lane == 0) {
+            if (prm.has_v) a.dvalue_raw[grow] = f.gv;
+            if (prm.has_r) a.dreturn_raw[grow] = f.gr;
+        }
+    }
+    HRL_STAMP(19);
+    zero_burn_in(prm, c);
+    __syncthreads();
+    if (s_last) finalize_losses(prm, L, smem, c);
+    HRL_STAMP(6);
+}
+
 // ======================================================================== bulk (TMA) kernel
 // Wide rows (A % 4 == 0).  A cluster of CS CTAs shares one window: CTA `crank` owns the time steps [t_lo, t_hi).
 //   * thread 0 issues one TMA bulk load per chunk of NC logit rows into zbuf right at the start -- the CTA's
@@ -779,6 +867,39 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
             return launch_bulk(prm, grid, NC * 32, best_bytes, stream);
         }
         HRL_REQUIRE(mode != 2, HRL_ERR_UNSUPPORTED, "hrl_loss_fwd_bwd: bulk kernel forced but the window does not fit");
+    }
+
+    // ---- group kernel: small action spaces, RL = 2^k >= A lanes per row (default for A <= 32)
+    if (a.A <= 32 && (mode == -1 || mode == 4)) {
+        const int RL = pow2_ceil(a.A);
+        const int lanes_ep = R * RL;
+        int EPB = lanes_ep >= 256 ? 1 : (256 + lanes_ep - 1) / lanes_ep;
+        if (EPB > a.B) EPB = a.B;
+        const int grid0 = (a.B + EPB - 1) / EPB;
+        int cap = 1024 / ((grid0 + kNumSM - 1) / kNumSM);      // keep the whole grid resident in one wave
+        cap = cap / 32 * 32;
+        int threads = ((EPB * lanes_ep + 31) / 32) * 32;
+        if (threads > cap) threads = cap;
+        if (threads > 1024) threads = 1024;
+        if (threads < 64) threads = 64;
+        threads = env_int("HRL_LOSS_THREADS", threads);
+        const SmemLayout L = make_layout(EPB, prm.Tt, a.P, a.Pa, 1, a.A, 0, -1, false, prm.scan + 1);
+        if ((size_t)L.total * 4 <= (size_t)100 * 1024) {
+            prm.EPB = EPB;
+            prm.stage_z = 1;
+            prm.row_stride = a.A;
+            HRL_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= 2048 + (size_t)grid0 * 8 * sizeof(float), HRL_ERR_WORKSPACE,
+                        "hrl_loss_fwd_bwd: workspace of %zu bytes is too small", a.workspace_bytes);
+            const size_t bytes = (size_t)L.total * 4;
+            switch (RL) {
+                case 1: return launch_kernel(loss_group_kernel<1>, prm, grid0, threads, bytes, stream);
+                case 2: return launch_kernel(loss_group_kernel<2>, prm, grid0, threads, bytes, stream);
+                case 4: return launch_kernel(loss_group_kernel<4>, prm, grid0, threads, bytes, stream);
+                case 8: return launch_kernel(loss_group_kernel<8>, prm, grid0, threads, bytes, stream);
+                case 16: return launch_kernel(loss_group_kernel<16>, prm, grid0, threads, bytes, stream);
+                default: return launch_kernel(loss_group_kernel<32>, prm, grid0, threads, bytes, stream);
+            }
+        }
     }
 
     // ---- element kernel: small action spaces

@@ -183,7 +183,7 @@ def test_both_recurrence_forms_match_reference(name, scan, monkeypatch):
 MODE_CASES = ['alt_UPGO_VTRACE', 'obs_TD_TD', 'geese4', 'wide', 'wide512', 'odd33', 'burnin_obs', 'novalue_ret', 'solo1']
 
 
-@pytest.mark.parametrize('mode', ['0', '1', '2', '3'], ids=['rows-direct', 'rows-staged', 'bulk', 'element'])
+@pytest.mark.parametrize('mode', ['0', '1', '2', '3', '4'], ids=['rows-direct', 'rows-staged', 'bulk', 'element', 'group'])
 @pytest.mark.parametrize('name', MODE_CASES)
 def test_every_kernel_variant_matches_reference(name, mode, monkeypatch):
     """HRL_LOSS_MODE forces one data-movement variant of the fused kernel (falling back to the direct rows kernel
