@@ -184,7 +184,8 @@ def reference_arm(opt, w):
     if w['net'] == 'geister':
         print(json.dumps({'impl': 'reference', 'unavailable': 'the CPU port (oracle/torch_learner.py) covers feed-forward nets only'}), flush=True)
         return
-    r = run_cpu_port(w, opt.steps, opt.warmup, budget_s=150.0)
+    # torchrun exports OMP_NUM_THREADS=1; the baseline gets the host's physical cores regardless (capped at 64)
+    r = run_cpu_port(w, opt.steps, opt.warmup, budget_s=150.0, threads=max(1, min(64, (os.cpu_count() or 2) // 2)))
     sample = '%d steps of a B=%d x T=%d batch (workload B=%d)' % (opt.steps, r['B_sample'], w['T'], w['B'])
     line = {
         'impl': 'reference', 'metric': 'learner_samples_per_sec', 'value': r['value'], 'unit': 'samples/s',
@@ -379,7 +380,7 @@ def b200_arm(opt, w):
             'kernel': loss_kernel_name(WORKLOADS['cfg5shard']['A']) + ' (hrl_loss_fwd_bwd)', 'kernel_us': wide['ms'] * 1e3,
             'algorithmic_bytes': wide['bytes'], 'traffic': None if traffic_all is None else traffic_all.get('cfg5shard')}
     if world == 1 and not opt.no_cpu and w['net'] != 'geister':     # the CPU port is feed-forward only
-        r = run_cpu_port(w, steps=8, warmup=1, budget_s=25.0)
+        r = run_cpu_port(w, steps=8, warmup=1, budget_s=25.0, threads=max(1, min(64, (os.cpu_count() or 2) // 2)))
         r1 = run_cpu_port(w, steps=4, warmup=1, budget_s=12.0, threads=1)
         line['cpu_baseline'] = {
             'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port',
