@@ -4,6 +4,7 @@
     handyrl_b200.ops       tensor-level wrappers of the C ABI (include/hrl_b200.h), FlatAdam, PeerAllReduce
     handyrl_b200.replay    GPU-resident replay + gather/pad kernel
     handyrl_b200.batch     host-side episode decoding and window sampling
+    handyrl_b200.wire      flat episode wire format for workers
     handyrl_b200.fastnet   small-board rewrite pass for user nets
     handyrl_b200.dist      multi-GPU sharding helpers
 

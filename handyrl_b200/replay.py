@@ -75,9 +75,10 @@ class DeviceReplay:
         return len(self.handles)
 
     def add(self, episode):
-        """Decode one episode dict of the reference's wire format (generation.py:84-91) and upload it."""
-        fe = flatten_moments(decode_moments(episode['moment']), episode['outcome'])
-        return self.add_flat(fe)
+        """Decode one episode dict (the reference's wire format, generation.py:84-91, or the flat format of
+        wire.py) and upload it."""
+        from .wire import episode_to_flat
+        return self.add_flat(episode_to_flat(episode))
 
     def add_flat(self, fe):
         if not self.ready:

@@ -582,7 +582,8 @@ class GpuBatcher:
                 ep = self.pending.get(timeout=0.2)
             except queue.Empty:
                 continue
-            fe = flatten_moments(decode_moments(ep['moment']), ep['outcome'])
+            from .wire import episode_to_flat
+            fe = episode_to_flat(ep)          # flat wire format if the worker sent it, else decode the moments
             with self.lock:
                 if self.last_gather is not None:
                     self.last_gather.synchronize()      # never overwrite rows an in-flight gather may read
@@ -758,8 +759,9 @@ class Trainer:
             self.stepper.stream.synchronize()
 
 
-def install():
-    """Swap the reference's learner hot path for this one in an importable `handyrl` package:
+def install(flat_episodes=False):
+    """Swap the reference's learner hot path for this one in an importable `handyrl` package
+    (flat_episodes=True additionally makes workers forked afterwards ship the flat wire format of wire.py):
     after `handyrl_b200.train.install()`, `python main.py --train` runs the reference's Learner,
     workers and server unchanged on top of this Trainer."""
     import handyrl.train as ref
@@ -770,4 +772,7 @@ def install():
     ref.compute_loss = compute_loss
     import handyrl.losses as ref_losses
     ref_losses.compute_target = ops.compute_target
+    if flat_episodes:
+        from .wire import install_worker_hook
+        install_worker_hook()
     return ref
