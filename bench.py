@@ -256,8 +256,6 @@ def b200_arm(opt, w):
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
         pg = dist.group.WORLD
-    torch.backends.cudnn.allow_tf32 = False          # fp32 throughout: parity with the reference's arithmetic
-    torch.backends.cuda.matmul.allow_tf32 = False
 
     args = train_args(w)
     B, T, P, A = w['B'], w['T'], w['P'], w['A']

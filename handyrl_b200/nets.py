@@ -119,3 +119,122 @@ class WideActionNet(nn.Module):
 
 def tictactoe_net():
     return BoardNet(planes=3, board=(3, 3), width=32, depth=3, actions=9)
+
+
+class ConvLstmCell(nn.Module):
+    """Convolutional LSTM cell: one 3x3 convolution over [input, h] produces the four gate maps
+    (order i, f, o, g along the channel axis, as in the reference's cell, geister.py:43-56)."""
+
+    def __init__(self, in_maps, state_maps, ksize=3):
+        super().__init__()
+        self.state_maps = state_maps
+        self.conv = nn.Conv2d(in_maps + state_maps, 4 * state_maps, ksize, padding=ksize // 2, bias=True)
+
+    def forward(self, x, state):
+        h, c = state
+        i, f, o, g = self.conv(torch.cat([x, h], dim=1)).chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        return torch.sigmoid(o) * torch.tanh(c), c
+
+
+class _MoveHead(nn.Module):
+    def __init__(self, maps, mid, out_maps):
+        super().__init__()
+        self.reduce = nn.Conv2d(maps, mid, 3, padding=1, bias=False)
+        self.norm = nn.BatchNorm2d(mid)
+        self.project = nn.Conv2d(mid, out_maps, 1, bias=False)
+
+    def forward(self, h):
+        return self.project(F.relu(self.norm(self.reduce(h)))).flatten(1)
+
+
+class _ScalarHead(nn.Module):
+    def __init__(self, maps, mid, cells, outputs):
+        super().__init__()
+        self.reduce = nn.Conv2d(maps, mid, 1, bias=False)
+        self.norm = nn.BatchNorm2d(mid)
+        self.out = nn.Linear(cells * mid, outputs, bias=False)
+
+    def forward(self, h):
+        return self.out(F.relu(self.norm(self.reduce(h))).flatten(1))
+
+
+class DrcBoardNet(nn.Module):
+    """Deep-repeated ConvLSTM net over a 6x6 board with a dict observation {'scalar': (18,), 'board': (7,6,6)}:
+    the architecture of the reference's GeisterNet (geister.py:66-98, 101-167) -- stem conv+BN over the scalar planes
+    stacked on the board planes, `depth` ConvLSTM cells applied `repeats` times per step (cell i > 0 reads the fresh
+    h of cell i-1), a 3x3-conv/BN/1x1-conv move head whose 4x36 logits are followed by 70 "set" logits computed
+    from the turn colour, and conv/BN/Linear value (tanh) and return heads.  231,604 parameters; its state_dict
+    has the reference's order and shapes, so reference weights load with `load_state_by_order`."""
+
+    def __init__(self, scalars=18, planes=7, board=(6, 6), width=32, depth=3, repeats=3, move_maps=4, set_actions=70):
+        super().__init__()
+        self.board, self.width, self.depth, self.repeats = tuple(board), width, depth, repeats
+        cells = board[0] * board[1]
+        self.stem = nn.Conv2d(scalars + planes, width, 3, padding=1, bias=False)
+        self.stem_norm = nn.BatchNorm2d(width)
+        self.cells = nn.ModuleList(ConvLstmCell(width, width) for _ in range(depth))
+        self.move_head = _MoveHead(width, 8, move_maps)
+        self.set_head = nn.Linear(1, set_actions, bias=True)
+        self.value_head = _ScalarHead(width, 2, cells, 1)
+        self.return_head = _ScalarHead(width, 2, cells, 1)
+
+    def init_hidden(self, batch_size=None):
+        shape = tuple(batch_size or []) + (self.width,) + self.board
+        return ([torch.zeros(shape) for _ in range(self.depth)], [torch.zeros(shape) for _ in range(self.depth)])
+
+    def forward(self, x, hidden):
+        board, scalar = x['board'], x['scalar']
+        planes = scalar[:, :, None, None].expand(-1, -1, *self.board)
+        e = F.relu(self.stem_norm(self.stem(torch.cat([planes, board], dim=1))))
+        if hidden is None:
+            hidden = self.init_hidden([board.shape[0]])
+            hidden = tuple([t.to(board.device) for t in part] for part in hidden)
+        hs, cs = list(hidden[0]), list(hidden[1])
+        for _ in range(self.repeats):
+            for i, cell in enumerate(self.cells):
+                hs[i], cs[i] = cell(hs[i - 1] if i > 0 else e, (hs[i], cs[i]))
+        top = hs[-1]
+        policy = torch.cat([self.move_head(top), self.set_head(scalar[:, :1])], dim=1)
+        return {'policy': policy, 'value': torch.tanh(self.value_head(top)), 'return': self.return_head(top),
+                'hidden': (hs, cs)}
+
+
+class _TorusBlock(nn.Module):
+    def __init__(self, in_maps, out_maps):
+        super().__init__()
+        # wrap-around padding on both board axes == the reference's explicit edge concatenation (hungry_geese.py:30-32)
+        self.conv = nn.Conv2d(in_maps, out_maps, 3, padding=1, padding_mode='circular')
+        self.bn = nn.BatchNorm2d(out_maps)
+
+    def forward(self, x):
+        return self.bn(self.conv(x))
+
+
+class TorusNet(nn.Module):
+    """Residual tower of wrap-around 3x3 convolutions over a 7x11 torus, policy from the features at the marked
+    head cell (observation plane 0), value from [head features, mean features]: the architecture of the reference's
+    GeeseNet (hungry_geese.py:23-57).  Same state_dict order and shapes, so reference weights load by order."""
+
+    def __init__(self, planes=17, width=32, depth=12, actions=4):
+        super().__init__()
+        self.stem = _TorusBlock(planes, width)
+        self.tower = nn.ModuleList(_TorusBlock(width, width) for _ in range(depth))
+        self.p_out = nn.Linear(width, actions, bias=False)
+        self.v_out = nn.Linear(2 * width, 1, bias=False)
+
+    def forward(self, x, hidden=None):
+        h = F.relu(self.stem(x))
+        for blk in self.tower:
+            h = F.relu(h + blk(h))
+        flat = h.flatten(2)
+        at_head = (flat * x[:, :1].flatten(2)).sum(-1)
+        return {'policy': self.p_out(at_head), 'value': torch.tanh(self.v_out(torch.cat([at_head, flat.mean(-1)], dim=1)))}
+
+
+def geister_net():
+    return DrcBoardNet()
+
+
+def geese_net():
+    return TorusNet()

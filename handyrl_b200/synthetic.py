@@ -104,6 +104,33 @@ def synthetic_batch(B, T, P, A, *, turn_based=True, observation=False, reward_ki
     return batch
 
 
+def synthetic_geister_batch(B, T, P, A, *, turn_based=True, observation=True, burn_in=0, seed=0):
+    """Geister-shaped batch: step rewards/returns and a dict observation {'scalar': (18,), 'board': (7,6,6)}
+    (the observation structure of geister.py:131-167)."""
+    batch = synthetic_batch(B, T, P, A, turn_based=turn_based, observation=observation, reward_kind='step',
+                            seed=seed, burn_in=burn_in, with_obs=False)
+    Pa = batch['action'].shape[2]
+    g = torch.Generator().manual_seed(seed + 7)
+    batch['observation'] = {'scalar': torch.rand((B, T, Pa, 18), generator=g),
+                            'board': (torch.rand((B, T, Pa, 7, 6, 6), generator=g) < 0.3).float()}
+    return batch
+
+
+def synthetic_geese_batch(B, T, P, A=4, *, seed=0, board=(7, 11), planes=17):
+    """Hungry-Geese-shaped batch (simultaneous layout, P = Pa players): 17 x 7 x 11 observations whose plane 0 marks
+    exactly one cell (the player's head, which the net's policy head reads, hungry_geese.py:50) and whose other
+    planes are sparse occupancy maps."""
+    batch = synthetic_batch(B, T, P, A, turn_based=False, observation=False, seed=seed, with_obs=False)
+    g = torch.Generator().manual_seed(seed + 11)
+    cells = board[0] * board[1]
+    obs = (torch.rand((B, T, P, planes, cells), generator=g) < 0.08).float()
+    head = torch.randint(0, cells, (B, T, P), generator=g)
+    obs[..., 0, :] = torch.nn.functional.one_hot(head, cells).float()
+    live = (batch['turn_mask'] > 0).view(B, T, P, 1, 1).float()
+    batch['observation'] = (obs * live).view(B, T, P, planes, *board)
+    return batch
+
+
 def synthetic_outputs(batch, *, has_value=True, has_return=False, seed=1):
     """Raw net outputs for kernel-only tests: policy ~ N(0,1), value = tanh(N(0,1))."""
     g = torch.Generator().manual_seed(seed)

@@ -227,9 +227,16 @@ class LearnerStep:
 
     def __init__(self, model, args, example_batch, lr, device=None, process_group=None, use_graph=True,
                  max_norm=4.0, weight_decay=1e-5, time_loss_kernel=False, channels_last=True, cudnn_benchmark=True,
-                 small_boards=True, peer_allreduce=None):
+                 small_boards=True, peer_allreduce=None, allow_tf32=None):
         self.device = torch.device(device if device is not None else 'cuda')
         self.args = args
+        # the learner owns its precision contract (1e-5 of the reference's fp32 arithmetic): PyTorch's default lets
+        # cuDNN convolutions run on TF32 tensor cores (10-bit mantissa).  train_args['allow_tf32'] = True opts out.
+        if allow_tf32 is None:
+            allow_tf32 = bool(args.get('allow_tf32', False))
+        self.allow_tf32 = allow_tf32
+        torch.backends.cudnn.allow_tf32 = allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = allow_tf32
         self.model = model.to(self.device)
         # cuDNN's default heuristics pick FFT / NCHW-spatial kernels that are 5x slower than its NHWC
         # implicit-GEMM kernels on the tiny boards of these games; NHWC + autotune is a pure layout choice

@@ -116,8 +116,47 @@ def loss_from_raw(raw, batch, args):
     return out, tm.sum()
 
 
+def _walk(fn, *trees):
+    t = trees[0]
+    if isinstance(t, dict):
+        return {k: _walk(fn, *[x[k] for x in trees]) for k in t}
+    if isinstance(t, (list, tuple)):
+        return type(t)(_walk(fn, *[x[i] for x in trees]) for i in range(len(t)))
+    return fn(*trees)
+
+
+def recurrent_raw_outputs(net, hidden, batch, args):
+    """The reference's sequential pass over T for nets with a hidden state (train.py:147-174): the hidden state is
+    masked by observation_mask before each call (summed over players in the turn-alternating layout), burn-in steps run
+    in eval mode without gradient, and the new hidden state replaces the old one only where the player observed."""
+    B, T, Pa = batch['action'].shape[:3]
+    alternating = args['turn_based_training'] and not args['observation']
+    rows = {}
+    for t in range(T):
+        obs = _walk(lambda o: o[:, t].flatten(0, 1), batch['observation'])
+        seen = batch['observation_mask'][:, t]
+        shaped = _walk(lambda h: seen.view(*h.shape[:2], *([1] * (h.dim() - 2))), hidden)
+        visible = _walk(lambda h, m: h * m, hidden, shaped)
+        visible = _walk((lambda h: h.sum(1)) if alternating else (lambda h: h.flatten(0, 1)), visible)
+        if t < args['burn_in_steps']:
+            net.eval()
+            with torch.no_grad():
+                out = net(obs, visible)
+        else:
+            if not net.training:
+                net.train()
+            out = net(obs, visible)
+        fresh = _walk(lambda h: h.unflatten(0, (B, Pa)), out.pop('hidden'))
+        for k, v in out.items():
+            if v is not None:
+                rows.setdefault(k, []).append(v.unflatten(0, (B, Pa)))
+        hidden = _walk(lambda h, n, m: h * (1 - m) + n * m, hidden, fresh, shaped)
+    return {k: torch.stack(v, 1) for k, v in rows.items()}
+
+
 class CpuLearner:
-    """Feed-forward learner step on the host: net forward -> loss -> autograd -> clip -> Adam."""
+    """Learner step on the host: net forward (one call, or the sequential pass for recurrent nets) -> loss ->
+    autograd -> clip -> Adam."""
 
     def __init__(self, net, args, lr, weight_decay=1e-5, max_norm=4.0):
         self.net, self.args, self.max_norm = net, args, max_norm
@@ -127,11 +166,15 @@ class CpuLearner:
 
     def step(self, batch):
         B, T, Pa = batch['action'].shape[:3]
-        outs = self.net(batch['observation'].flatten(0, 2), None)
-        raw = {k: v.unflatten(0, (B, T, Pa)) for k, v in outs.items() if v is not None and k != 'hidden'}
+        if hasattr(self.net, 'init_hidden'):
+            P = batch['turn_mask'].shape[2]
+            raw = recurrent_raw_outputs(self.net, self.net.init_hidden([B, P]), batch, self.args)
+        else:
+            outs = self.net(_walk(lambda o: o.flatten(0, 2), batch['observation']), None)
+            raw = {k: v.unflatten(0, (B, T, Pa)) for k, v in outs.items() if v is not None and k != 'hidden'}
         losses, dcnt = loss_from_raw(raw, batch, self.args)
         self.opt.zero_grad()
         losses['total'].backward()
-        torch.nn.utils.clip_grad_norm_(self.params, self.max_norm)
+        self.grad_norm = float(torch.nn.utils.clip_grad_norm_(self.params, self.max_norm))
         self.opt.step()
         return {k: float(v.detach()) for k, v in losses.items()}, float(dcnt)

@@ -47,3 +47,27 @@ def loss_cases():
 @pytest.fixture(scope='session')
 def target_cases():
     return load_cases('target_cases.npz')
+
+
+def net_case_setup(case):
+    """(stand-in net loaded with the reference's initial weights, [three seeded batches]) for a net_step_cases.pkl case."""
+    from handyrl_b200 import nets
+    from handyrl_b200.synthetic import synthetic_geese_batch, synthetic_geister_batch
+    B, T, P, A = case['dims']
+    args = case['args']
+    if case['net'] == 'geister':
+        net = nets.load_state_by_order(nets.geister_net(), case['state0'])
+        batches = [synthetic_geister_batch(B, T, P, A, turn_based=args['turn_based_training'], observation=args['observation'],
+                                           burn_in=args['burn_in_steps'], seed=s) for s in case['seeds']]
+    else:
+        net = nets.load_state_by_order(nets.geese_net(), case['state0'])
+        batches = [synthetic_geese_batch(B, T, P, A, seed=s) for s in case['seeds']]
+    return net, batches
+
+
+def noise_driven(case, key):
+    """Weights whose gradient is analytically ZERO -- the bias of a convolution that feeds straight into BatchNorm
+    (GeeseNet's TorusConv2d, hungry_geese.py:23-35) -- receive Adam updates of ~lr*sign(rounding noise): two equally valid
+    fp32 runs disagree on them by up to 2*lr per step, and nothing downstream depends on them except that BatchNorm's
+    running mean, which absorbs the bias.  Skipped in weight checks."""
+    return case['net'] == 'geese' and (key.endswith('conv.bias') or key.endswith('bn.running_mean'))

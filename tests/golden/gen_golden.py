@@ -10,6 +10,8 @@ Outputs (committed):
     tests/golden/batch_cases.pkl    make_batch on real self-play episodes (train.py:33-124)
     tests/golden/step_cases.pkl     3 full optimiser steps of the reference Trainer maths (train.py:366-371)
     tests/golden/rnn_cases.pkl      recurrent forward_prediction + compute_loss + parameter gradients (train.py:147-174)
+    tests/golden/net_step_cases.pkl 3 optimiser steps of the reference's GeisterNet (DRC ConvLSTM, recurrent path) and
+                                    GeeseNet (torus convolutions; `kaggle_environments` stubbed)
 
 The reference has no golden vectors of its own for this path, so the
 vectors are the reference's own outputs.  The fp64 quirk of `selected_prob` is avoided by
@@ -294,10 +296,78 @@ def gen_rnn_cases():
     print('rnn cases:', list(out))
 
 
+def _reference_steps(net, args, batches, hidden_fn, lr=1e-4):
+    """Three optimiser steps exactly as Trainer.train does them (train.py:358-371)."""
+    import torch.nn as nn
+    import torch.optim as optim
+    state0 = {k: v.clone().numpy() for k, v in net.state_dict().items()}
+    params = list(net.parameters())
+    opt = optim.Adam(params, lr=lr, weight_decay=1e-5)
+    wrapped = ModelWrapper(net)
+    wrapped.train()
+    steps = []
+    for batch in batches:
+        losses, dcnt = ref_train.compute_loss(batch, wrapped, hidden_fn(wrapped, batch), args)
+        opt.zero_grad()
+        losses['total'].backward()
+        gnorm = nn.utils.clip_grad_norm_(params, 4.0)
+        opt.step()
+        steps.append({'losses': {k: float(v.item()) for k, v in losses.items()}, 'dcnt': float(dcnt),
+                      'grad_norm': float(gnorm)})
+    return state0, steps, {k: v.clone().numpy() for k, v in net.state_dict().items()}
+
+
+def geister_batch(B, T, P, A, turn_based, observation, burn_in, seed):
+    from handyrl_b200.synthetic import synthetic_geister_batch
+    return synthetic_geister_batch(B, T, P, A, turn_based=turn_based, observation=observation, burn_in=burn_in, seed=seed)
+
+
+def gen_net_step_cases():
+    """configs[2] / configs[3] of BASELINE.json with the reference's own networks."""
+    import types
+    from handyrl.envs.geister import GeisterNet
+    stub = types.ModuleType('kaggle_environments')      # the env cannot run here; only the net is needed
+    stub.make = lambda *a, **k: None
+    sys.modules.setdefault('kaggle_environments', stub)
+    from handyrl.envs.kaggle.hungry_geese import GeeseNet
+    out = {}
+    for name, (turn_based, observation) in {'geister_obs': (True, True), 'geister_alt': (True, False)}.items():
+        torch.manual_seed(5)
+        net = GeisterNet()
+        B, T, P, A, burn_in = 6, 6, 2, 214, 2
+        args = {'turn_based_training': turn_based, 'observation': observation, 'gamma': 0.8, 'lambda': 0.7,
+                'burn_in_steps': burn_in, 'forward_steps': T - burn_in, 'entropy_regularization': 0.1,
+                'entropy_regularization_decay': 0.1, 'policy_target': 'TD', 'value_target': 'TD', 'batch_size': B}
+        batches = [geister_batch(B, T, P, A, turn_based, observation, burn_in, 60 + s) for s in range(3)]
+        state0, steps, state3 = _reference_steps(net, args, batches, lambda w, b: w.init_hidden([B, P]))
+        # lr 1e-4: Adam's first steps move every weight by ~lr*sign(g), so weights whose gradient is rounding noise
+        # (e.g. conv biases in front of BatchNorm: analytically zero) diverge by 2*lr between equally valid fp32 runs
+        out[name] = {'net': 'geister', 'args': args, 'dims': (B, T, P, A), 'seeds': [60, 61, 62], 'state0': state0,
+                     'steps': steps, 'lr': 1e-4, 'state3': state3}
+    torch.manual_seed(6)
+    net = GeeseNet()
+    B, T, P, A = 8, 4, 4, 4
+    args = {'turn_based_training': False, 'observation': False, 'gamma': 0.8, 'lambda': 0.7, 'burn_in_steps': 0,
+            'forward_steps': T, 'entropy_regularization': 0.1, 'entropy_regularization_decay': 0.1,
+            'policy_target': 'VTRACE', 'value_target': 'VTRACE', 'batch_size': B}
+    from handyrl_b200.synthetic import synthetic_geese_batch
+    batches = [synthetic_geese_batch(B, T, P, A, seed=80 + s) for s in range(3)]
+    state0, steps, state3 = _reference_steps(net, args, batches, lambda w, b: None)
+    out['geese'] = {'net': 'geese', 'args': args, 'dims': (B, T, P, A), 'seeds': [80, 81, 82], 'state0': state0,
+                    'steps': steps, 'lr': 1e-4, 'state3': state3}
+    with open(os.path.join(HERE, 'net_step_cases.pkl'), 'wb') as f:
+        pickle.dump(out, f)
+    print('net step cases:', list(out))
+
+
 if __name__ == '__main__':
     os.chdir('/tmp')
+    if len(sys.argv) > 1 and sys.argv[1] == 'nets':
+        gen_net_step_cases()
+        sys.exit(0)
     gen_loss_cases()
     gen_target_cases()
     gen_batch_cases()
     gen_step_cases()
     gen_rnn_cases()
+    gen_net_step_cases()

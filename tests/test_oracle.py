@@ -112,3 +112,28 @@ def test_torch_port_full_steps_match_reference():
                 assert abs(losses[k] - v) <= 1e-5 * abs(v) + 1e-5, (name, s, k)
         for (k, v), (kr, vr) in zip(net.state_dict().items(), c['state3'].items()):
             np.testing.assert_allclose(v.numpy(), vr, rtol=1e-5, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.parametrize('name', ['geister_obs', 'geister_alt', 'geese'])
+def test_torch_port_and_net_standins_match_reference_nets(name):
+    """The architecture stand-ins (DRC ConvLSTM = GeisterNet, torus tower = GeeseNet) driven by the CPU port reproduce three
+    optimiser steps of the reference's own networks, recurrent path (burn-in, hidden masking) included."""
+    import os
+    import pickle
+    from conftest import GOLDEN, net_case_setup, noise_driven
+    from oracle.torch_learner import CpuLearner
+    with open(os.path.join(GOLDEN, 'net_step_cases.pkl'), 'rb') as f:
+        c = pickle.load(f)[name]
+    net, batches = net_case_setup(c)
+    lrn = CpuLearner(net, c['args'], lr=c['lr'])
+    for s, (batch, ref) in enumerate(zip(batches, c['steps'])):
+        losses, dcnt = lrn.step(batch)
+        assert dcnt == ref['dcnt']
+        scale = max(abs(v) for v in ref['losses'].values())     # `total` is a difference of the larger terms
+        for k, v in ref['losses'].items():
+            assert abs(losses[k] - v) <= 1e-5 * scale + 1e-5, (name, s, k, losses[k], v)
+        assert abs(lrn.grad_norm - ref['grad_norm']) <= 1e-3 * ref['grad_norm']
+    for (k, v), (kr, vr) in zip(net.state_dict().items(), c['state3'].items()):
+        if noise_driven(c, k):
+            continue
+        np.testing.assert_allclose(v.numpy(), vr, rtol=1e-4, atol=2e-5, err_msg='%s/%s' % (k, kr))   # Adam turns 1e-9 gradient noise into ~1e-6 weight noise

@@ -15,15 +15,48 @@ with open(os.path.join(GOLDEN, 'step_cases.pkl'), 'rb') as f:
     STEP_CASES = pickle.load(f)
 with open(os.path.join(GOLDEN, 'rnn_cases.pkl'), 'rb') as f:
     RNN_CASES = pickle.load(f)
+with open(os.path.join(GOLDEN, 'net_step_cases.pkl'), 'rb') as f:
+    NET_CASES = pickle.load(f)
 
 
 @pytest.fixture(autouse=True)
-def exact_fp32():
+def default_precision_flags():
+    """PyTorch's defaults (cuDNN TF32 allowed): LearnerStep itself must switch to full fp32, not the harness."""
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = True
     torch.backends.cuda.matmul.allow_tf32 = False
     yield
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize('use_graph', [False, True], ids=['eager', 'graph'])
+@pytest.mark.parametrize('name', sorted(NET_CASES))
+def test_three_learner_steps_match_reference_geister_and_geese_nets(name, use_graph):
+    """BASELINE configs[2]/[3] architectures (DRC ConvLSTM with burn-in and hidden masking; 12-block torus tower) through
+    LearnerStep: losses, gradient norm and final weights of three optimiser steps of the reference's own GeisterNet /
+    GeeseNet (weights loaded by order into the stand-ins)."""
+    from conftest import net_case_setup, noise_driven
+    from handyrl_b200.train import LearnerStep
+    c = NET_CASES[name]
+    net, batches = net_case_setup(c)
+    stepper = LearnerStep(net, c['args'], batches[0], lr=c['lr'], use_graph=use_graph)
+    assert torch.backends.cudnn.allow_tf32 is False
+    for s, (batch, ref) in enumerate(zip(batches, c['steps'])):
+        stepper.step(stepper.new_packed().fill(batch))
+        got = stepper.read_losses()
+        scale = max(abs(v) for v in ref['losses'].values())
+        for k, v in ref['losses'].items():
+            assert abs(got[k] - v) <= 1e-4 * scale + 1e-4, (s, k, got[k], v)
+        assert got['dcnt'] == ref['dcnt']
+        assert abs(float(stepper.opt.grad_norm) - ref['grad_norm']) <= 2e-3 * ref['grad_norm']
+    final = stepper.cpu_state_dict()
+    for (k, v), (kr, vr) in zip(final.items(), c['state3'].items()):
+        if noise_driven(c, k):
+            continue
+        if v.dtype.is_floating_point:
+            np.testing.assert_allclose(v.numpy(), vr, rtol=1e-3, atol=5e-5, err_msg='%s/%s' % (k, kr))
+        else:
+            assert int(v) == int(vr)
 
 
 @pytest.mark.parametrize('use_graph', [False, True], ids=['eager', 'graph'])
@@ -60,6 +93,7 @@ def test_recurrent_compute_loss_and_param_grads(name):
     from handyrl_b200.nets import GatedBoardNet
     from handyrl_b200.train import compute_loss
     c = RNN_CASES[name]
+    torch.backends.cudnn.allow_tf32 = False      # the bare drop-in function leaves backend flags to its caller
     net = GatedBoardNet()
     net.load_state_dict({k: torch.from_numpy(v) for k, v in c['state0'].items()})
     net = net.cuda().train()
