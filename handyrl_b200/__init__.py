@@ -6,7 +6,7 @@
     handyrl_b200.batch     host-side episode decoding and window sampling
     handyrl_b200.wire      flat episode wire format for workers
     handyrl_b200.fastnet   small-board rewrite pass for user nets
-    handyrl_b200.dist      multi-GPU sharding helpers
+    handyrl_b200.multigpu  multi-GPU learner: helper ranks behind Trainer, sharding helpers
 
 The CUDA library (handyrl_b200/libhrl_b200.so) is built by `__graft_entry__.build()`; there is no CPU fallback.
 """

@@ -207,11 +207,13 @@ def make_batch(episodes, args):
     return tree_map(lambda a: torch.from_numpy(np.ascontiguousarray(a)), np_batch)
 
 
-def sample_window(n_episodes, steps_of, args, rng=random):
+def sample_window(n_episodes, fetch, args, rng=random):
     """Recency-biased episode choice + window placement (train.py:291-308).
 
-    Returns (episode index, start, end, train_start).  `steps_of(idx)` gives the episode length
-    and may raise IndexError if the replay shrank concurrently (train.py:298-302 retries).
+    `fetch(idx)` returns (steps, episode) for the idx-th oldest episode and may raise IndexError if the replay
+    shrank concurrently (train.py:298-302 retries).  The episode object is fetched ONCE and handed back, so the
+    window always fits the episode it was drawn for even when the deque shifts underneath.
+    Returns (episode index, start, end, train_start, episode).
     """
     while True:
         count = min(n_episodes(), args['maximum_episodes'])
@@ -220,7 +222,7 @@ def sample_window(n_episodes, steps_of, args, rng=random):
         if rng.random() >= accept:
             continue
         try:
-            steps = steps_of(idx)
+            steps, episode = fetch(idx)
         except IndexError:
             continue
         break
@@ -228,4 +230,4 @@ def sample_window(n_episodes, steps_of, args, rng=random):
     train_start = rng.randrange(candidates)
     start = max(0, train_start - args['burn_in_steps'])
     end = min(train_start + args['forward_steps'], steps)
-    return idx, start, end, train_start
+    return idx, start, end, train_start, episode

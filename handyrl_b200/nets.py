@@ -19,13 +19,16 @@ class BoardNet(nn.Module):
     """
 
     def __init__(self, planes=3, board=(3, 3), width=32, depth=3, actions=9, policy_maps=2, value_maps=1,
-                 return_head=False):
+                 return_head=False, norm=True):
         super().__init__()
         cells = board[0] * board[1]
         self.stem = nn.Conv2d(planes, width, 3, padding=1)
         self.tower = nn.ModuleList()
         for _ in range(depth):
-            self.tower.append(nn.Sequential(nn.Conv2d(width, width, 3, padding=1, bias=False), nn.BatchNorm2d(width)))
+            if norm:
+                self.tower.append(nn.Sequential(nn.Conv2d(width, width, 3, padding=1, bias=False), nn.BatchNorm2d(width)))
+            else:       # no batch statistics: a sharded step is then exactly the full-batch step (multi-GPU parity tests)
+                self.tower.append(nn.Sequential(nn.Conv2d(width, width, 3, padding=1, bias=True)))
         self.p_squeeze = nn.Conv2d(width, policy_maps, 1)
         self.p_out = nn.Linear(cells * policy_maps, actions, bias=False)
         self.v_squeeze = nn.Conv2d(width, value_maps, 1)

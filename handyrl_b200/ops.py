@@ -162,7 +162,8 @@ class FlatAdam:
     all-reduce).
     """
 
-    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, max_norm=4.0, extra=0, grad_alloc=None):
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, max_norm=4.0, extra=0, grad_alloc=None,
+                 param_storage=None):
         params = [p for p in params]
         assert len(params) > 0 and all(p.is_cuda and p.dtype == torch.float32 for p in params)
         self.params = params
@@ -170,7 +171,11 @@ class FlatAdam:
         self.n = sum(p.numel() for p in params)
         n_pad = (self.n + 3) // 4 * 4
         self.extra = extra
-        self.flat_param = torch.zeros(n_pad, dtype=torch.float32, device=device)
+        # param_storage lets the caller place the weights inside a larger state buffer (LearnerStep: weights + BatchNorm
+        # buffers in one allocation, so the per-epoch model hand-off is ONE device-to-host copy)
+        if param_storage is not None:
+            assert param_storage.numel() == n_pad and param_storage.dtype == torch.float32 and param_storage.data_ptr() % 16 == 0
+        self.flat_param = param_storage if param_storage is not None else torch.zeros(n_pad, dtype=torch.float32, device=device)
         extra = (extra + 3) // 4 * 4
         self.extra = extra
         # grad_alloc(numel) lets the caller place the bucket in NVLink-symmetric memory (peer all-reduce)

@@ -12,7 +12,7 @@ Nested observations are stored as the concatenation of their flattened leaves.
 """
 import ctypes as C
 import random
-from collections import deque
+import threading
 
 import numpy as np
 import torch
@@ -27,10 +27,17 @@ assert WINDOW_DTYPE.itemsize == C.sizeof(HrlWindow)
 
 
 class EpisodeHandle:
+    """Where one stored episode lives: first row of the step ring, number of steps, row of the outcome table."""
     __slots__ = ('first_step', 'steps', 'outcome_row')
 
     def __init__(self, first_step, steps, outcome_row):
-        self.first_step, self.steps, self.outcome_row = first_step, steps, outcome_row
+        self.first_step, self.steps, self.outcome_row = int(first_step), int(steps), int(outcome_row)
+
+    def __eq__(self, other):
+        return (self.first_step, self.steps, self.outcome_row) == (other.first_step, other.steps, other.outcome_row)
+
+    def __repr__(self):
+        return 'EpisodeHandle(first_step=%d, steps=%d, outcome_row=%d)' % (self.first_step, self.steps, self.outcome_row)
 
 
 class DeviceReplay:
@@ -38,16 +45,41 @@ class DeviceReplay:
 
     capacity_steps bounds the stored steps, max_episodes the stored episodes (the reference trims its
     deque to `maximum_episodes`, train.py:474-483); when either is exceeded the oldest episodes go.
+    The episode directory (first row / length / outcome row, oldest first) is a numpy ring so that B windows
+    are drawn with array operations instead of a Python loop per window.
     """
 
     def __init__(self, capacity_steps, max_episodes, device='cuda'):
         self.device = torch.device(device)
         self.capacity = int(capacity_steps)
         self.max_episodes = int(max_episodes)
-        self.handles = deque()
+        self._dir = np.zeros((self.max_episodes + 1, 3), np.int64)      # (first_step, steps, outcome_row), a ring
+        self._head = 0
+        self._count = 0
         self.write = 0
         self.ready = False
         self.next_outcome_row = 0
+        self.lock = threading.Lock()       # guards the directory (feeder thread appends, learner thread samples)
+
+    # ------------------------------------------------------------------ directory
+    def __len__(self):
+        return self._count
+
+    def _entry(self, i):
+        return self._dir[(self._head + i) % self._dir.shape[0]]
+
+    @property
+    def handles(self):
+        """Stored episodes, oldest first (a snapshot; the directory itself is the numpy ring)."""
+        return [EpisodeHandle(*self._entry(i)) for i in range(self._count)]
+
+    def _popleft(self):
+        self._head = (self._head + 1) % self._dir.shape[0]
+        self._count -= 1
+
+    def _append(self, first_step, steps, row):
+        self._dir[(self._head + self._count) % self._dir.shape[0]] = (first_step, steps, row)
+        self._count += 1
 
     def _allocate(self, fe):
         S, dev = self.capacity, self.device
@@ -57,6 +89,8 @@ class DeviceReplay:
         self.leaf_shapes = [tuple(l.shape[2:]) for l in tree_leaves(fe.obs)]
         self.leaf_sizes = [int(np.prod(s)) if len(s) else 1 for s in self.leaf_shapes]
         self.OE = int(sum(self.leaf_sizes))
+        if fe.value.shape[-1] != 1:
+            raise ValueError('DeviceReplay stores a scalar behaviour value per player; got %d values' % fe.value.shape[-1])
         f = dict(dtype=torch.float32, device=dev)
         self.st_obs = torch.zeros((S, self.Ps, self.OE), **f)
         self.st_prob = torch.ones((S, self.Ps), **f)
@@ -71,8 +105,12 @@ class DeviceReplay:
         self.st_outcome = torch.zeros((self.n_outcome_rows, self.Ps), **f)
         self.ready = True
 
-    def __len__(self):
-        return len(self.handles)
+    @staticmethod
+    def bytes_per_step(fe):
+        """HBM bytes one stored step of this kind of episode takes (sizing the ring from free memory)."""
+        Ps = len(fe.players)
+        OE = sum(int(np.prod(l.shape[2:])) if l.ndim > 2 else 1 for l in tree_leaves(fe.obs))
+        return Ps * (4 * OE + 4 * fe.amask.shape[-1] + 4 * 5 + 1) + 4
 
     def add(self, episode):
         """Decode one episode dict (the reference's wire format, generation.py:84-91, or the flat format of
@@ -81,41 +119,79 @@ class DeviceReplay:
         return self.add_flat(episode_to_flat(episode))
 
     def add_flat(self, fe):
+        return self.add_flat_many([fe])[0]
+
+    def add_flat_many(self, fes):
+        """Upload several decoded episodes (stage + commit)."""
+        return self.commit(self.stage(fes)) if fes else []
+
+    def stage(self, fes):
+        """Host half of an upload: concatenate the episodes' step rows column by column into page-locked staging
+        tensors.  Touches neither the ring nor the directory, so a feeder thread can do it without holding any lock
+        the learner needs."""
         if not self.ready:
-            self._allocate(fe)
-        n = fe.steps
-        if n > self.capacity:
-            raise ValueError('episode of %d steps exceeds the replay capacity of %d steps' % (n, self.capacity))
-        if self.write + n > self.capacity:          # episodes are stored contiguously: wrap
-            # the previous lap's episodes beyond the write pointer are the oldest ones: drop them so
-            # that deque order == ring order again
-            while self.handles and self.handles[0].first_step >= self.write:
-                self.handles.popleft()
-            self.write = 0
-        lo, hi = self.write, self.write + n
-        # evict whatever the new rows overwrite, and the oldest episode beyond max_episodes
-        while self.handles and (len(self.handles) >= self.max_episodes or
-                                (self.handles[0].first_step < hi and self.handles[0].first_step + self.handles[0].steps > lo)):
-            self.handles.popleft()
-        dev = self.device
-        obs = np.concatenate([l.reshape(n, self.Ps, -1).astype(np.float32) for l in tree_leaves(fe.obs)], axis=2)
-        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
-        self.st_obs[lo:hi] = up(obs)
-        self.st_prob[lo:hi] = up(fe.prob)
-        self.st_action[lo:hi] = up(fe.action)
-        self.st_amask[lo:hi] = up(fe.amask)
-        self.st_value[lo:hi] = up(fe.value[..., 0])
-        self.st_reward[lo:hi] = up(fe.reward)
-        self.st_return[lo:hi] = up(fe.ret)
-        self.st_flags[lo:hi] = up(fe.flags)
-        self.st_turn[lo:hi] = up(fe.turn)
-        row = self.next_outcome_row
-        self.next_outcome_row = (row + 1) % self.n_outcome_rows
-        self.st_outcome[row] = up(fe.outcome)
-        h = EpisodeHandle(lo, n, row)
-        self.handles.append(h)
-        self.write = hi
-        return h
+            self._allocate(fes[0])
+        pin = self.device.type == 'cuda'
+
+        def host(parts, dtype):
+            a = np.concatenate(parts) if len(parts) > 1 else parts[0]
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype))
+            return t.pin_memory() if pin else t
+
+        cols = {
+            'obs': host([np.concatenate([l.reshape(fe.steps, self.Ps, -1).astype(np.float32, copy=False)
+                                         for l in tree_leaves(fe.obs)], axis=2) for fe in fes], np.float32),
+            'prob': host([fe.prob for fe in fes], np.float32), 'action': host([fe.action for fe in fes], np.int32),
+            'amask': host([fe.amask for fe in fes], np.float32), 'value': host([fe.value[..., 0] for fe in fes], np.float32),
+            'reward': host([fe.reward for fe in fes], np.float32), 'return': host([fe.ret for fe in fes], np.float32),
+            'flags': host([fe.flags for fe in fes], np.uint8), 'turn': host([fe.turn for fe in fes], np.int32),
+        }
+        return {'steps': [int(fe.steps) for fe in fes], 'cols': cols,
+                'outcome': host([np.stack([fe.outcome for fe in fes])], np.float32)}
+
+    def commit(self, staged):
+        """Device half of an upload: place the staged episodes in the ring (evicting what they overwrite and the
+        oldest episodes beyond max_episodes) and enqueue the copies on the current stream.  Rows are placed back to
+        back, so every run of episodes that does not cross the end of the ring is ONE copy per store column."""
+        handles, segments = [], []        # segments: [dst_lo, src_lo, n]
+        rows = []
+        with self.lock:
+            src = 0
+            for n in staged['steps']:
+                if n > self.capacity:
+                    raise ValueError('episode of %d steps exceeds the replay capacity of %d steps' % (n, self.capacity))
+                if self.write + n > self.capacity:          # episodes are stored contiguously: wrap
+                    # the previous lap's episodes beyond the write pointer are the oldest ones: drop them so
+                    # that directory order == ring order again
+                    while self._count and self._entry(0)[0] >= self.write:
+                        self._popleft()
+                    self.write = 0
+                lo, hi = self.write, self.write + n
+                # evict whatever the new rows overwrite, and the oldest episode beyond max_episodes
+                while self._count and (self._count >= self.max_episodes or
+                                       (self._entry(0)[0] < hi and self._entry(0)[0] + self._entry(0)[1] > lo)):
+                    self._popleft()
+                row = self.next_outcome_row
+                self.next_outcome_row = (row + 1) % self.n_outcome_rows
+                if segments and segments[-1][0] + segments[-1][2] == lo:
+                    segments[-1][2] += n
+                else:
+                    segments.append([lo, src, n])
+                rows.append(row)
+                self._append(lo, n, row)
+                handles.append(EpisodeHandle(lo, n, row))
+                self.write = hi
+                src += n
+            store = {'obs': self.st_obs, 'prob': self.st_prob, 'action': self.st_action, 'amask': self.st_amask,
+                     'value': self.st_value, 'reward': self.st_reward, 'return': self.st_return, 'flags': self.st_flags,
+                     'turn': self.st_turn}
+            for dst_lo, src_lo, n in segments:
+                for k, t in store.items():
+                    t[dst_lo:dst_lo + n].copy_(staged['cols'][k][src_lo:src_lo + n], non_blocking=True)
+            idx = torch.tensor(rows, dtype=torch.long)
+            self.st_outcome.index_copy_(0, idx.to(self.device, non_blocking=True),
+                                        staged['outcome'].to(self.device, non_blocking=True))
+        return handles
 
     # ------------------------------------------------------------------ batches
     def batch_shapes(self, args):
@@ -140,13 +216,38 @@ class DeviceReplay:
         }
 
     def sample_windows(self, B, args, rng=random):
-        """B window descriptors drawn like Batcher.select_episode (train.py:291-315)."""
-        win = np.zeros(B, WINDOW_DTYPE)
+        """B window descriptors drawn like Batcher.select_episode (train.py:291-315).
+
+        rng = a numpy Generator: all B windows are drawn with array operations (the learner's path: the same
+        recency-biased acceptance law and uniform window placement, B at a time).
+        rng = the `random` module / a random.Random: the reference's own call sequence, window by window, so a seeded
+        stream reproduces the reference's picks exactly (tests)."""
         solo = not args['turn_based_training']
-        for b in range(B):
-            idx, st, ed, tst = sample_window(lambda: len(self.handles), lambda i: self.handles[i].steps, args, rng)
-            h = self.handles[idx]
-            win[b] = (h.first_step, st, ed, tst, h.steps, h.outcome_row, 0)
+        win = np.zeros(B, WINDOW_DTYPE)
+        if isinstance(rng, np.random.Generator):
+            with self.lock:
+                count = min(self._count, args['maximum_episodes'])
+                if count <= 0:
+                    raise IndexError('the replay is empty')
+                idx = np.empty(0, np.int64)
+                while idx.size < B:           # accept idx with probability (idx+1)/count (train.py:294-297)
+                    cand = rng.integers(0, count, size=2 * (B - idx.size) + 8)
+                    idx = np.concatenate([idx, cand[rng.random(cand.size) < (cand + 1) / count]])
+                ent = self._dir[(self._head + idx[:B]) % self._dir.shape[0]]
+            steps = ent[:, 1]
+            train_start = (rng.random(B) * (1 + np.maximum(0, steps - args['forward_steps']))).astype(np.int64)
+            win['first_step'], win['total'], win['outcome_row'] = ent[:, 0], steps, ent[:, 2]
+            win['train_start'] = train_start
+            win['start'] = np.maximum(0, train_start - args['burn_in_steps'])
+            win['end'] = np.minimum(train_start + args['forward_steps'], steps)
+            if solo:
+                win['player'] = rng.integers(0, self.Ps, size=B)
+            return win
+        with self.lock:
+            for b in range(B):
+                _, st, ed, tst, ent = sample_window(lambda: self._count, lambda i: (self._entry(i)[1], self._entry(i).copy()),
+                                                    args, rng)
+                win[b] = (ent[0], st, ed, tst, ent[1], ent[2], 0)
         if solo:
             for b in range(B):          # make_batch draws the solo player per window, in order (train.py:57-58)
                 win[b]['player'] = rng.choice(range(self.Ps))
@@ -159,7 +260,10 @@ class DeviceReplay:
         T, P, Pa, alternating = self.batch_shapes(args)
         if out is None:
             out = self.empty_batch(B, args)
-        wdev = torch.from_numpy(windows.view(np.uint8).reshape(B, -1)).to(self.device, non_blocking=True)
+        if torch.is_tensor(windows):          # descriptors already staged on the device (pinned double buffering)
+            wdev = windows
+        else:
+            wdev = torch.from_numpy(windows.view(np.uint8).reshape(B, -1)).to(self.device, non_blocking=True)
         g = HrlGatherArgs()
         g.B, g.T, g.P, g.Pa, g.A, g.Ps = B, T, P, Pa, self.A, self.Ps
         g.burn_in = args['burn_in_steps']

@@ -13,17 +13,21 @@ Same public names as handyrl/train.py for the path
     is captured in a CUDA graph and replayed; the host never synchronises inside an epoch
     (the reference does 4-6 .item() syncs per step, train.py:200, 375-376).
 """
+import collections
 import copy
 import os
+import pickle
 import queue
 import threading
 import time
+import traceback
 from collections import deque
 
+import numpy as np
 import torch
 
 from . import ops, fastnet
-from .batch import tree_map, tree_leaves, make_batch, flatten_moments, decode_moments, gather_windows, sample_window
+from .batch import tree_map, tree_leaves, make_batch, gather_windows, sample_window
 from ._capi import LOSS_KEYS, NUM_LOSS
 
 
@@ -216,6 +220,100 @@ class PackedBatch:
             self.in_flight = None
 
 
+class StateStore:
+    """Everything `model.state_dict()` holds, in ONE device allocation: [fp32 parameters, padded to 4 | fp32 buffers
+    (BatchNorm running statistics) | int64 buffers (num_batches_tracked)].  Parameters and buffers are re-pointed
+    into it, so the per-epoch model hand-off to the workers (train.py:385-387) is one device-to-device snapshot on
+    the step stream plus one device-to-host copy on a side stream instead of a `model.cpu()` of every tensor."""
+
+    def __init__(self, model, device):
+        params = list(model.parameters())
+        self.n = sum(p.numel() for p in params)
+        self.n_pad = (self.n + 3) // 4 * 4
+        named = list(model.named_buffers())
+        fbufs = [(k, b) for k, b in named if b.dtype == torch.float32]
+        ibufs = [(k, b) for k, b in named if b.dtype == torch.int64]
+        self.loose = [(k, b) for k, b in named if b.dtype not in (torch.float32, torch.int64)]   # copied one by one
+        nf = sum(b.numel() for _, b in fbufs)
+        ni = sum(b.numel() for _, b in ibufs)
+        self.f_off = 4 * self.n_pad
+        self.i_off = (self.f_off + 4 * nf + 7) // 8 * 8
+        self.nbytes = self.i_off + 8 * ni
+        self.bytes = torch.zeros(max(self.nbytes, 16), dtype=torch.uint8, device=device)
+        self.flat_param = self.bytes[:4 * self.n_pad].view(torch.float32)
+        fview = self.bytes[self.f_off:self.f_off + 4 * nf].view(torch.float32)
+        iview = self.bytes[self.i_off:self.i_off + 8 * ni].view(torch.int64)
+        self.where = {}           # state_dict key -> (view name, offset in elements, shape)
+        with torch.no_grad():
+            for view, tag, bufs in ((fview, 'f', fbufs), (iview, 'i', ibufs)):
+                off = 0
+                for k, b in bufs:
+                    n = b.numel()
+                    view[off:off + n].copy_(b.reshape(-1))
+                    b.data = view[off:off + n].view(b.shape)
+                    self.where[k] = (tag, off, tuple(b.shape))
+                    off += n
+        self._params = params
+
+    def index_params(self, model):
+        """Call after FlatAdam re-pointed the parameters into flat_param (same order as model.parameters())."""
+        off = 0
+        for k, p in model.named_parameters():
+            self.where[k] = ('p', off, tuple(p.shape))
+            off += p.numel()
+
+    def state_dict_from(self, host_bytes, keys):
+        """Rebuild {key: CPU tensor} from a host copy of `bytes` (fresh storage per tensor)."""
+        views = {'p': host_bytes[:4 * self.n_pad].view(torch.float32),
+                 'f': host_bytes[self.f_off:self.i_off].view(torch.float32) if self.i_off > self.f_off else None,
+                 'i': host_bytes[self.i_off:self.nbytes].view(torch.int64) if self.nbytes > self.i_off else None}
+        out = {}
+        for k in keys:
+            if k in self.where:
+                tag, off, shape = self.where[k]
+                n = 1
+                for d in shape:
+                    n *= d
+                out[k] = views[tag][off:off + n].clone().view(shape)
+        return out
+
+
+class PendingModel:
+    """The model of a finished epoch, still on its way to the host.  `resolve()` (called by Trainer.update() on the
+    Learner's thread) waits for the side-stream copy only, prints the epoch's loss line, rebuilds the CPU model in
+    eval mode and caches its pickled bytes on it (the Learner pickles the model for every worker request,
+    train.py:605-615)."""
+
+    def __init__(self, stepper, done_event, host_state, host_losses, heads, template):
+        self.stepper, self.done, self.host_state, self.host_losses = stepper, done_event, host_state, host_losses
+        self.heads, self.template = heads, template
+
+    def resolve(self):
+        self.done.synchronize()
+        sums = dict(zip(LOSS_KEYS, self.host_losses.tolist()))
+        dcnt = sums['dcnt']
+        if dcnt > 0:
+            print('loss = %s' % ' '.join([k + ':' + '%.3f' % (sums[k] / dcnt) for k in self.heads]))
+        tpl = self.template
+        state = self.stepper.state.state_dict_from(self.host_state, tpl.state_dict().keys())
+        for k, b in self.stepper.state.loose:
+            state[k] = b.detach().cpu()
+        tpl.load_state_dict(state)
+        tpl.eval()
+        blob = pickle.dumps(tpl)
+        model = pickle.loads(blob)                        # == copy.deepcopy(tpl), and leaves the bytes for the workers
+        attach_pickle_cache(model, blob)
+        return model, sums
+
+
+def attach_pickle_cache(model, blob):
+    """pickle.dumps(model) / copy.deepcopy(model) of this instance replay `blob` instead of walking the module tree:
+    the instance-level __reduce_ex__ makes every later pickle of the (immutable until the next epoch) model a memcpy.
+    What the workers unpickle is the plain nn.Module that `blob` holds."""
+    object.__setattr__(model, '__reduce_ex__', lambda protocol, _b=blob: (pickle.loads, (_b,)))
+    return model
+
+
 class LearnerStep:
     """One replay batch -> one optimiser step.
 
@@ -259,8 +357,18 @@ class LearnerStep:
         if peer_allreduce is None:
             peer_allreduce = self.world > 1 and os.environ.get('HRL_PEER_ALLREDUCE', '1') != '0'
         self.peer = ops.PeerAllReduce(self.pg, self.device) if (peer_allreduce and self.world > 1) else None
+        self.state = StateStore(self.model, self.device)
         self.opt = ops.FlatAdam(params, lr=lr, weight_decay=weight_decay, max_norm=max_norm, extra=NUM_LOSS,
-                                grad_alloc=self.peer.alloc if self.peer is not None else None)
+                                grad_alloc=self.peer.alloc if self.peer is not None else None,
+                                param_storage=self.state.flat_param)
+        self.state.index_params(self.model)
+        self.state_snap = torch.empty_like(self.state.bytes)
+        self.acc_snap = torch.zeros(NUM_LOSS, dtype=torch.float64, device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._handoff_slots = None
+        self._handoff_i = 0
+        self.ema = torch.full((1,), float(example_batch['action'].shape[0] * args.get('forward_steps', 1)) * self.world,
+                              dtype=torch.float32, device=self.device)
 
         self.layout = BatchLayout(example_batch)
         self.dev_buffer = torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=self.device)
@@ -456,18 +564,95 @@ class LearnerStep:
         torch.cuda.synchronize(self.device)
 
     def cpu_state_dict(self):
+        """Blocking copy of the model's state_dict to the host (tests, checkpoints)."""
         self.stream.synchronize()
-        return {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items() if not k.endswith('_sel_cache')}
+        host = self.state.bytes.cpu()
+        keys = [k for k in self.model.state_dict().keys() if not k.endswith('_sel_cache')]
+        out = self.state.state_dict_from(host, keys)
+        for k, b in self.state.loose:
+            out[k] = b.detach().cpu().clone()
+        return {k: out[k] for k in keys}
+
+    def epoch_schedule(self, batch_cnt, steps, default_lr):
+        """Device half of the epoch boundary, on the current stream: move the epoch's loss sums aside and apply the
+        learning-rate schedule from the (all-reduced, hence global) data count.  Every rank of a sharded learner
+        enqueues this at the same step, so all ranks keep identical learning rates without a broadcast."""
+        self.acc_snap.copy_(self.loss_accum)
+        self.loss_accum.zero_()
+        dcnt = self.acc_snap[5:6].float()
+        fresh = self.ema * 0.8 + dcnt * (0.2 / (1e-2 + batch_cnt))
+        self.ema.copy_(torch.where(dcnt > 0, fresh, self.ema))
+        self.opt.lr.copy_(self.ema * (default_lr / (1 + steps * 1e-5)))
+
+    def end_epoch(self, batch_cnt, steps, default_lr, template, heads):
+        """Epoch boundary without a host synchronisation (train.py:378-387): on the step stream, snapshot the loss
+        sums and the whole model state device-to-device, apply the learning-rate schedule ON THE DEVICE
+        (data_cnt_ema <- 0.8 ema + 0.2 dcnt/(0.01+batch_cnt); lr <- 3e-8 ema/(1+steps 1e-5), train.py:382-384 -- dcnt is
+        the all-reduced global count) and let a side stream carry the snapshot to pinned host memory while the
+        next epoch's steps already run.  Returns a PendingModel."""
+        if self._handoff_slots is None:
+            self._handoff_slots = [(torch.empty(self.state.bytes.numel(), dtype=torch.uint8).pin_memory(),
+                                    torch.zeros(NUM_LOSS, dtype=torch.float64).pin_memory()) for _ in range(2)]
+        host_state, host_losses = self._handoff_slots[self._handoff_i % 2]
+        self._handoff_i += 1
+        with torch.cuda.stream(self.stream):
+            self.epoch_schedule(batch_cnt, steps, default_lr)
+            if getattr(self, '_last_done', None) is not None:
+                self.stream.wait_event(self._last_done)          # the previous snapshot has left the device buffer
+            self.state_snap.copy_(self.state.bytes)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ready)
+            host_state.copy_(self.state_snap, non_blocking=True)
+            host_losses.copy_(self.acc_snap, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.copy_stream)
+        self._last_done = done
+        return PendingModel(self, done, host_state, host_losses, heads, template)
 
 
 # --------------------------------------------------------------------------- batcher + trainer
+
+class _FlatCache:
+    """Decoded episodes for the host batcher, least-recently-used first, bounded in bytes (the reference keeps only
+    the bz2 blocks, train.py:54; an unbounded cache of decoded arrays would grow to tens of GB at
+    maximum_episodes = 100000 and trip the Learner's memory guard)."""
+
+    def __init__(self, budget_bytes):
+        self.budget, self.used = int(budget_bytes), 0
+        self.items = collections.OrderedDict()       # id(episode) -> (episode, FlatEpisode, bytes)
+        self.lock = threading.Lock()
+
+    @staticmethod
+    def _size(fe):
+        return sum(a.nbytes for a in tree_leaves(fe.obs)) + fe.amask.nbytes + fe.value.nbytes + 24 * fe.prob.size
+
+    def get(self, ep):
+        from .wire import episode_to_flat
+        key = id(ep)
+        with self.lock:
+            hit = self.items.get(key)
+            if hit is not None and hit[0] is ep:
+                self.items.move_to_end(key)
+                return hit[1]
+        fe = episode_to_flat(ep)          # flat wire format if the worker sent it, else decode the moments
+        size = self._size(fe)
+        with self.lock:
+            self.items[key] = (ep, fe, size)
+            self.used += size
+            while self.used > self.budget and len(self.items) > 1:
+                _, (_, _, sz) = self.items.popitem(last=False)
+                self.used -= sz
+        return fe
+
 
 class Batcher:
     """Feeds the trainer: recency-biased window sampling (train.py:291-315) and collation.
 
     Unlike the reference there is no process pool shipping pickled batches through pipes
     (train.py:274, connection.py:133-173): episodes are decoded once into FlatEpisode arrays
-    (cached on the episode dict) and batches are built by `num_batchers` threads with numpy
+    (a byte-bounded LRU cache) and batches are built by `num_batchers` threads with numpy
     gathers that release the GIL.
     """
 
@@ -478,28 +663,24 @@ class Batcher:
         self.threads = []
         self.started = False
         self.stop_event = threading.Event()
+        self.cache = _FlatCache(args.get('host_cache_bytes', 2 << 30))
+
+    def _fetch(self, idx):
+        ep = self.episodes[idx]           # ONE read: the deque may shift under us (train.py:298-302)
+        return ep['steps'], ep
 
     def select_episode(self):
-        idx, st, ed, tst = sample_window(lambda: len(self.episodes), lambda i: self.episodes[i]['steps'], self.args)
-        ep = self.episodes[idx]
+        idx, st, ed, tst, ep = sample_window(lambda: len(self.episodes), self._fetch, self.args)
         cs = self.args['compress_steps']
         b0, b1 = st // cs, (ed - 1) // cs + 1
         return {'args': ep['args'], 'outcome': ep['outcome'], 'moment': ep['moment'][b0:b1], 'base': b0 * cs,
                 'start': st, 'end': ed, 'train_start': tst, 'total': ep['steps'], '_episode': ep}
 
-    @staticmethod
-    def _flat(ep):
-        fe = ep.get('_flat')
-        if fe is None:
-            fe = flatten_moments(decode_moments(ep['moment']), ep['outcome'])
-            ep['_flat'] = fe
-        return fe
-
     def _make(self):
         windows = []
         for _ in range(self.args['batch_size']):
             sel = self.select_episode()
-            fe = self._flat(sel['_episode'])
+            fe = self.cache.get(sel['_episode'])
             windows.append((fe, sel['start'], sel['end'], sel['start'], sel['train_start'], sel['total']))
         nb = gather_windows(windows, self.args)
         return tree_map(lambda a: torch.from_numpy(a), nb)
@@ -507,7 +688,12 @@ class Batcher:
     def _worker(self, bid):
         print('started batcher %d' % bid)
         while not self.stop_event.is_set():
-            item = self._make()
+            try:
+                item = self._make()
+            except Exception:              # a batcher thread must never die silently: Batcher.batch() would spin forever
+                traceback.print_exc()
+                time.sleep(0.05)
+                continue
             while not self.stop_event.is_set():
                 try:
                     self.out.put(item, timeout=0.2)
@@ -559,24 +745,73 @@ class EpisodeDeque(deque):
 
 class GpuBatcher:
     """Batcher on the GPU-resident replay (replay.py + the gather/pad kernel): arriving episodes are decoded once
-    by a feeder thread and uploaded into the device ring; a batch is B window descriptors (host RNG, same sampling
-    law as Batcher.select_episode) + ONE kernel that writes straight into the learner step's input buffer."""
+    by a feeder thread and uploaded into the device ring; a batch is B window descriptors (drawn with array
+    operations, same sampling law as Batcher.select_episode) + ONE kernel that writes straight into the learner
+    step's input buffer.
 
-    def __init__(self, args, episodes, device):
+    Feeder and learner never wait for each other's GPU work on the host: the upload stream waits (on the device) for
+    the last gather that may read rows it overwrites, the step stream waits for the last upload; the only shared
+    host lock covers "sample + enqueue gather" on one side and "update directory + enqueue copies" on the other
+    (microseconds each: staging into pinned memory happens outside it)."""
+
+    DESC_SLOTS = 4        # pinned descriptor buffers in rotation: bounds how far the host runs ahead of the GPU
+
+    def __init__(self, args, episodes, device, seed=None, forward=None):
         from .replay import DeviceReplay
+        from .wire import episode_to_flat
         self.args = args
         self.device = device
-        cap = int(args.get('replay_capacity_steps', 0)) or min(args['maximum_episodes'] * 64, 4_000_000)
-        self.replay = DeviceReplay(cap, args['maximum_episodes'], device=device)
+        self.forward = forward              # multi-GPU: callable(list of episodes) that ships them to the other ranks
         self.pending = queue.Queue()
         self.upload_stream = torch.cuda.Stream(device=device)
         self.last_upload = None
         self.last_gather = None
-        self.lock = threading.Lock()
+        self.order_lock = threading.Lock()
         self.stop_event = threading.Event()
-        episodes.listener = self.pending.put        # tap first, then the backlog: nothing is missed
-        for ep in list(episodes):
+        self.rng = np.random.default_rng(seed if seed is not None else args.get('seed', 0) * 7919 + 17)
+        self.fed = 0
+        self._slots = None
+        self._slot_i = 0
+
+        # tap first, then the backlog: nothing is missed; what the tap saw meanwhile is not enqueued twice, and the
+        # backlog keeps its (recency) order ahead of it
+        tapped, tap_lock = [], threading.Lock()
+
+        def tap(ep):
+            with tap_lock:
+                if tapped is not None and self._backlog_open:
+                    tapped.append(ep)
+                    return
             self.pending.put(ep)
+
+        self._backlog_open = True
+        episodes.listener = tap
+        backlog = list(episodes)
+        with tap_lock:
+            seen = {id(e) for e in tapped}
+            backlog = [e for e in backlog if id(e) not in seen] + tapped
+            self._backlog_open = False
+        for ep in backlog:
+            self.pending.put(ep)
+        self.backlog_n = len(backlog)
+
+        # ring capacity from the observed episode lengths and the free HBM (the reference bounds episodes, not steps)
+        fe0 = episode_to_flat(backlog[0]) if backlog else None
+        cap = int(args.get('replay_capacity_steps', 0))
+        if not cap:
+            lens = [e['steps'] for e in backlog] or [64]
+            mean_len, max_len = sum(lens) / len(lens), max(lens)
+            want = int(args['maximum_episodes'] * mean_len * 1.25) + 4 * max_len
+            budget = want
+            if fe0 is not None and torch.device(device).type == 'cuda':
+                free, _ = torch.cuda.mem_get_info(device)
+                budget = int(args.get('replay_memory_fraction', 0.5) * free / DeviceReplay.bytes_per_step(fe0))
+            cap = max(4 * max_len, min(want, budget))
+            est = int(cap / max(mean_len, 1))
+            if est < args['maximum_episodes']:
+                print('handyrl_b200: the GPU replay holds about %d episodes (%d steps), fewer than maximum_episodes=%d'
+                      % (est, cap, args['maximum_episodes']))
+        self.replay = DeviceReplay(cap, args['maximum_episodes'], device=device)
         self.thread = threading.Thread(target=self._feed, daemon=True)
 
     def run(self):
@@ -584,33 +819,62 @@ class GpuBatcher:
             self.thread.start()
 
     def _feed(self):
+        from .wire import episode_to_flat
         while not self.stop_event.is_set():
             try:
-                ep = self.pending.get(timeout=0.2)
+                eps = [self.pending.get(timeout=0.2)]
             except queue.Empty:
                 continue
-            from .wire import episode_to_flat
-            fe = episode_to_flat(ep)          # flat wire format if the worker sent it, else decode the moments
-            with self.lock:
-                if self.last_gather is not None:
-                    self.last_gather.synchronize()      # never overwrite rows an in-flight gather may read
-                with torch.cuda.stream(self.upload_stream):
-                    self.replay.add_flat(fe)
-                    ev = torch.cuda.Event()
-                    ev.record(self.upload_stream)
-                    self.last_upload = ev
+            while len(eps) < 256:            # everything that has queued up goes in one upload
+                try:
+                    eps.append(self.pending.get_nowait())
+                except queue.Empty:
+                    break
+            try:
+                if self.forward is not None:
+                    self.forward(eps)
+                staged = self.replay.stage([episode_to_flat(ep) for ep in eps])
+                with self.order_lock:
+                    if self.last_gather is not None:   # device-side: never overwrite rows an enqueued gather reads
+                        self.upload_stream.wait_event(self.last_gather)
+                    with torch.cuda.stream(self.upload_stream):
+                        self.replay.commit(staged)
+                        ev = torch.cuda.Event()
+                        ev.record(self.upload_stream)
+                        self.last_upload = ev
+            except Exception:
+                traceback.print_exc()
+            self.fed += len(eps)
 
     def ready(self):
-        return len(self.replay) > 0
+        """True once the whole backlog the trainer started with is resident (the reference samples from at least
+        `minimum_episodes` episodes from its first step on)."""
+        return self.fed >= self.backlog_n and len(self.replay) > 0
+
+    def _descriptor_slot(self, B):
+        from .replay import WINDOW_DTYPE
+        if self._slots is None:
+            nb = B * WINDOW_DTYPE.itemsize
+            self._slots = [{'host': torch.empty(nb, dtype=torch.uint8).pin_memory(),
+                            'dev': torch.empty((B, WINDOW_DTYPE.itemsize), dtype=torch.uint8, device=self.device),
+                            'event': None} for _ in range(self.DESC_SLOTS)]
+        slot = self._slots[self._slot_i % self.DESC_SLOTS]
+        self._slot_i += 1
+        if slot['event'] is not None:
+            slot['event'].synchronize()      # the gather that read this slot DESC_SLOTS steps ago
+        return slot
 
     def fill(self, stepper):
         """Sample a batch and gather it into stepper.dev (on the step stream)."""
-        B = self.args['batch_size']
-        with self.lock:
-            win = self.replay.sample_windows(B, self.args)
+        B = stepper.dims[0]
+        slot = self._descriptor_slot(B)
+        with self.order_lock:
+            win = self.replay.sample_windows(B, self.args, self.rng)
+            slot['host'].numpy()[:] = win.view(np.uint8)
             with torch.cuda.stream(stepper.stream):
                 if self.last_upload is not None:
                     stepper.stream.wait_event(self.last_upload)
+                slot['dev'].view(-1).copy_(slot['host'], non_blocking=True)
                 out = dict(stepper.dev)
                 single_leaf = torch.is_tensor(stepper.dev['observation'])
                 if single_leaf:
@@ -618,7 +882,7 @@ class GpuBatcher:
                 else:
                     out['observation'] = self._flat_obs(stepper)
                 out['value'] = self._value_sink(stepper)
-                self.replay.gather(win, self.args, out=out)
+                self.replay.gather(slot['dev'], self.args, out=out)
                 if not single_leaf:
                     nested = self.replay.split_observation(out['observation'])
                     for d, s_ in zip(tree_leaves(stepper.dev['observation']), tree_leaves(nested)):
@@ -626,6 +890,7 @@ class GpuBatcher:
                 ev = torch.cuda.Event()
                 ev.record(stepper.stream)
                 self.last_gather = ev
+                slot['event'] = ev
 
     def _flat_obs(self, stepper):
         if not hasattr(self, '_obs_buf'):
@@ -647,7 +912,12 @@ class GpuBatcher:
 
 class Trainer:
     """Drop-in for handyrl.train.Trainer (train.py:321-400): same constructor, attributes
-    (`episodes`, `steps`), `run()` thread body and `update()` hand-off, same printed lines."""
+    (`episodes`, `steps`), `run()` thread body and `update()` hand-off, same printed lines.
+
+    Multi-GPU (the reference wraps its model in nn.DataParallel when it sees several GPUs, train.py:325, 339-340):
+    with train_args['num_gpus'] > 1 (default: every visible GPU, as the reference) this process is rank 0 and spawns
+    one helper process per further GPU (multigpu.py); every rank holds the whole replay, samples batch_size/num_gpus
+    windows per step and the gradient bucket is all-reduced (SUM) inside the captured step."""
 
     def __init__(self, args, model):
         self.episodes = EpisodeDeque()
@@ -664,43 +934,75 @@ class Trainer:
         self.update_flag = False
         self.update_queue = queue.Queue(maxsize=1)
         self.stepper = None
+        self.fleet = None
         self.stop_event = threading.Event()
         if len(self.params) > 0 and not torch.cuda.is_available():
             raise RuntimeError('handyrl_b200.Trainer needs a CUDA device; there is no CPU learner in this package')
+        self.world = 1
+        if len(self.params) > 0:
+            want = args.get('num_gpus')
+            self.world = max(1, min(int(want), torch.cuda.device_count()) if want else torch.cuda.device_count())
+            if self.world > 1 and (not self.gpu_replay or args['batch_size'] % self.world != 0):
+                print('handyrl_b200: multi-GPU needs gpu_replay and batch_size %% num_gpus == 0; using one GPU')
+                self.world = 1
 
     def update(self):
-        self.update_flag = True
-        model, steps = self.update_queue.get()
+        """Called by the Learner (train.py:342-345, 533): ends the running epoch and returns (CPU model in eval
+        mode, steps).  The trainer thread only enqueues the hand-off; the wait for the side-stream copy, the
+        state_dict rebuild and the pickling happen here, on the caller's thread."""
+        while True:
+            self.update_flag = True
+            item, steps = self.update_queue.get()
+            if not isinstance(item, PendingModel):
+                return item, steps
+            model, sums = item.resolve()
+            if sums['dcnt'] > 0:           # train.py:357: an epoch needs at least one sample with a turn in it
+                break
+        # host mirrors of the schedule the device applied (train.py:382-384), for inspection / logging
+        self.data_cnt_ema = self.data_cnt_ema * 0.8 + sums['dcnt'] / (1e-2 + item.batch_cnt) * 0.2
+        self.lr = self.default_lr * self.data_cnt_ema / (1 + steps * 1e-5)
         return model, steps
 
-    def _cpu_model(self):
-        self.cpu_template.load_state_dict(self.stepper.cpu_state_dict())
+    def _start_stepper(self):
+        # the first batch is built on the host: it fixes every shape of the captured step
+        batch = self._first_host_batch()
+        self.cpu_template = copy.deepcopy(self.model)
         self.cpu_template.eval()
-        return copy.deepcopy(self.cpu_template)
+        pg = None
+        if self.world > 1:
+            from . import multigpu
+            batch = tree_map(lambda t: t[:t.shape[0] // self.world].contiguous(), batch)
+            self.fleet = multigpu.Fleet(self.world, self.args, self.cpu_template, list(self.episodes), self.lr)
+            pg = self.fleet.process_group
+        self.stepper = LearnerStep(self.model, self.args, batch, self.lr, process_group=pg)
+        self.stepper.warm_up()
+        self.batcher.pool = [self.stepper.new_packed() for _ in range(4)]
+        if self.gpu_replay:
+            self.gpu_batcher = GpuBatcher(self.args, self.episodes, self.stepper.device,
+                                          forward=self.fleet.send_episodes if self.fleet is not None else None)
+            self.gpu_batcher.run()
+        loss_buf = self.stepper.loss_buf
+        self.heads = ['p'] + (['v'] if loss_buf.dvalue is not None else []) + \
+            (['r'] if loss_buf.dreturn is not None else []) + ['ent', 'total']
 
     def train(self):
         if len(self.params) == 0:          # non-parametric model (train.py:348-350)
             time.sleep(0.1)
             return self.model
-        batch_cnt, data_cnt, loss_sum = 0, 0, {}
+        batch_cnt = 0
+        chunk = int(self.args.get('multi_gpu_chunk', 8))
         while True:
-            if self.stop_event.is_set():
-                return None
+            if self.stop_event.is_set() and (self.fleet is None or batch_cnt % chunk == 0):
+                return None                 # (sharded: only between chunks -- the other ranks run whole chunks)
             if self.stepper is None:
-                # the first batch is built on the host: it fixes every shape of the captured step
-                batch = self._first_host_batch()
-                self.cpu_template = copy.deepcopy(self.model)
-                self.stepper = LearnerStep(self.model, self.args, batch, self.lr)
-                self.stepper.warm_up()
-                self.batcher.pool = [self.stepper.new_packed() for _ in range(4)]
-                if self.gpu_replay:
-                    self.gpu_batcher = GpuBatcher(self.args, self.episodes, self.stepper.device)
-                    self.gpu_batcher.run()
+                self._start_stepper()
             if self.gpu_batcher is not None:
-                while not self.gpu_batcher.ready():
+                while not (self.gpu_batcher.ready() and (self.fleet is None or self.fleet.all_ready())):
                     if self.stop_event.is_set():
                         return None
                     time.sleep(0.01)
+                if self.fleet is not None and batch_cnt % chunk == 0:
+                    self.fleet.run_steps(chunk)          # every rank runs exactly the steps rank 0 runs
                 self.gpu_batcher.fill(self.stepper)
                 self.stepper.step_in_place()
             else:
@@ -713,21 +1015,14 @@ class Trainer:
                 self.stepper.step(packed)
             batch_cnt += 1
             self.steps += 1
-            if self.update_flag:            # ONE host sync per epoch instead of 4-6 per step
-                acc = self.stepper.pop_accumulated()
-                data_cnt += acc.pop('dcnt')
-                for k, v in acc.items():
-                    loss_sum[k] = loss_sum.get(k, 0.0) + v
-                if data_cnt > 0:
-                    break
-        heads = ['p'] + (['v'] if self.stepper.loss_buf.dvalue is not None else []) + \
-            (['r'] if self.stepper.loss_buf.dreturn is not None else []) + ['ent', 'total']
-        print('loss = %s' % ' '.join([k + ':' + '%.3f' % (loss_sum[k] / data_cnt) for k in heads]))
-
-        self.data_cnt_ema = self.data_cnt_ema * 0.8 + data_cnt / (1e-2 + batch_cnt) * 0.2
-        self.lr = self.default_lr * self.data_cnt_ema / (1 + self.steps * 1e-5)
-        self.stepper.opt.set_lr(self.lr)
-        return self._cpu_model()
+            if self.update_flag and (self.fleet is None or batch_cnt % chunk == 0):
+                break
+        # epoch boundary: nothing here waits for the GPU (LearnerStep.end_epoch)
+        if self.fleet is not None:
+            self.fleet.end_epoch(batch_cnt, self.steps, self.default_lr)
+        pending = self.stepper.end_epoch(batch_cnt, self.steps, self.default_lr, self.cpu_template, self.heads)
+        pending.batch_cnt = batch_cnt
+        return pending
 
     def _first_host_batch(self):
         return self.batcher._make()
@@ -757,13 +1052,17 @@ class Trainer:
 
     def stop(self):
         """Not in the reference (its threads die with the process): lets tests and embedders shut the
-        trainer down cleanly -- stops the batcher threads and ends run()."""
+        trainer down cleanly -- stops the batcher threads, the helper ranks, and ends run()."""
         self.stop_event.set()
         self.batcher.stop()
         if self.gpu_batcher is not None:
             self.gpu_batcher.stop()
         if self.stepper is not None:
             self.stepper.stream.synchronize()
+        if self.fleet is not None:
+            self.fleet.stop()
+            self.stepper.close()
+            self.fleet.destroy()
 
 
 def install(flat_episodes=False):

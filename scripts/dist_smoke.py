@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
-from handyrl_b200 import dist as hdist
+from handyrl_b200 import multigpu as hdist
 from handyrl_b200.nets import tictactoe_net
 from handyrl_b200.synthetic import synthetic_batch
 from handyrl_b200.train import LearnerStep

@@ -15,6 +15,21 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
+def pytest_collection_modifyitems(config, items):
+    """GPU tests are skipped, not failed, on a machine without a CUDA device (the product has no CPU path)."""
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason='needs a CUDA device')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
 def load_cases(fname):
     """Golden .npz -> {case: {key: array}} (+ parsed 'meta' dict when present)."""
     z = np.load(os.path.join(GOLDEN, fname), allow_pickle=False)

@@ -44,5 +44,6 @@ def test_sample_window_replays_reference_sampler():
     eps, args = case['episodes'], case['args']
     random.seed(5)
     for sel in case['selected']:
-        idx, st, ed, tst = sample_window(lambda: len(eps), lambda i: eps[i]['steps'], args)
+        idx, st, ed, tst, ep = sample_window(lambda: len(eps), lambda i: (eps[i]['steps'], eps[i]), args)
+        assert ep is eps[idx]
         assert (st, ed, tst, eps[idx]['steps']) == (sel['start'], sel['end'], sel['train_start'], sel['total'])

@@ -47,7 +47,7 @@ def bucket_for(batch):
 def worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
-    from handyrl_b200 import dist as hdist
+    from handyrl_b200 import multigpu as hdist
     from handyrl_b200.synthetic import synthetic_batch
     r, w, _ = hdist.init_from_env('gloo')
     assert (r, w) == (rank, world)
@@ -82,7 +82,7 @@ def test_sum_allreduce_of_shards_equals_full_batch():
 
 
 def test_shard_bounds_cover_the_batch():
-    from handyrl_b200.dist import shard_bounds
+    from handyrl_b200.multigpu import shard_bounds
     for B in (1, 7, 512, 4096):
         for world in (1, 2, 3, 8):
             spans = [shard_bounds(B, r, world) for r in range(world)]

@@ -119,7 +119,7 @@ def test_trainer_thread_protocol(gpu_replay):
         case = pickle.load(f)['tictactoe']
     args = dict(case['args'], batch_size=8, minimum_episodes=4, num_batchers=1, **{'lambda': 0.7},
                 entropy_regularization=0.1, entropy_regularization_decay=0.1, policy_target='UPGO', value_target='VTRACE',
-                gpu_replay=gpu_replay)
+                gpu_replay=gpu_replay, num_gpus=1)
     tr = Trainer(args, tictactoe_net())
     tr.episodes.extend(case['episodes'])
     th = threading.Thread(target=tr.run, daemon=True)
@@ -173,7 +173,7 @@ def test_trainer_on_geister_episodes_with_gpu_replay():
         case = pickle.load(f)['geister_burnin']
     args = dict(case['args'], batch_size=6, minimum_episodes=4, num_batchers=1, **{'lambda': 0.7},
                 entropy_regularization=0.1, entropy_regularization_decay=0.1, policy_target='TD', value_target='TD',
-                gpu_replay=True)
+                gpu_replay=True, num_gpus=1)
     net = GatedBoardNet(scalars=18, planes=7, board=(6, 6), width=8, actions=214)
     tr = Trainer(args, net)
     tr.episodes.extend(case['episodes'])
@@ -184,6 +184,103 @@ def test_trainer_on_geister_episodes_with_gpu_replay():
     assert all(torch.isfinite(p).all() for p in model.parameters())
     model2, steps2 = tr.update()
     assert steps2 > steps
+    tr.stop()
+    th.join(timeout=10)
+    assert not th.is_alive()
+
+
+def test_epoch_hand_off_never_synchronises_the_step_stream_and_workers_can_unpickle_it():
+    """f-4 (train.py:385-387, 605-615): update() may not stall the step stream; the model it returns pickles from cached
+    bytes and unpickles, in a process WITHOUT CUDA, to the plain module class in eval mode on the CPU."""
+    import pickle as pk
+    import subprocess
+    import sys
+    import threading
+    import time
+    from handyrl_b200.train import Trainer
+    from handyrl_b200.nets import tictactoe_net, BoardNet
+    with open(os.path.join(GOLDEN, 'batch_cases.pkl'), 'rb') as f:
+        case = pickle.load(f)['tictactoe']
+    args = dict(case['args'], batch_size=8, minimum_episodes=4, num_batchers=1, **{'lambda': 0.7}, num_gpus=1,
+                entropy_regularization=0.1, entropy_regularization_decay=0.1, policy_target='UPGO', value_target='VTRACE')
+    tr = Trainer(args, tictactoe_net())
+    tr.episodes.extend(case['episodes'])
+    th = threading.Thread(target=tr.run, daemon=True)
+    th.start()
+    tr.update()                                   # first epoch: builds and captures the step
+    stream_cls = type(tr.stepper.stream)
+    calls = []
+    real = stream_cls.synchronize
+    stream_cls.synchronize = lambda self: (calls.append(self), real(self))[1]
+    try:
+        steps_before = tr.steps
+        model, steps = tr.update()
+        time.sleep(0.05)
+    finally:
+        stream_cls.synchronize = real
+    assert not any(s is tr.stepper.stream for s in calls)          # the step stream was never synchronised
+    assert steps >= steps_before and type(model) is BoardNet and not model.training
+    assert all(p.device.type == 'cpu' for p in model.parameters())
+    assert tr.steps >= steps                                       # and training went on while we resolved the model
+    t0 = time.perf_counter()
+    blobs = [pk.dumps(model) for _ in range(200)]                  # Learner.server: one pickle per worker request
+    per_pickle = (time.perf_counter() - t0) / 200
+    assert per_pickle < 2e-3, per_pickle
+    code = ('import sys, pickle, torch; sys.path.insert(0, %r); m = pickle.loads(sys.stdin.buffer.read()); '
+            'assert not torch.cuda.is_available() and type(m).__name__ == "BoardNet" and not m.training; '
+            'print("OUT", float(m(torch.ones(1, 3, 3, 3))["value"]))' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = subprocess.run([sys.executable, '-c', code], input=blobs[0], capture_output=True, timeout=300,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=''))
+    assert res.returncode == 0, res.stderr.decode()[-2000:]
+    assert abs(float(res.stdout.decode().split('OUT')[1]) - float(model(torch.ones(1, 3, 3, 3))['value'])) < 1e-6
+    # the weights handed over are exactly the learner's weights at that step boundary or later ones, never torn
+    model2, _ = tr.update()
+    assert any(not torch.equal(a, b) for a, b in zip(model.state_dict().values(), model2.state_dict().values()))
+    tr.stop()
+    th.join(timeout=10)
+    assert not th.is_alive()
+
+
+def test_flat_wire_episodes_through_the_gpu_replay_feeder_under_a_live_learner():
+    """f-2 on the GPU + the Learner's side of the protocol: episodes in the flat wire format (moments dropped) arrive from
+    another thread while the trainer runs, the deque is trimmed as Learner.feed_episodes does (train.py:476-483), and
+    several epochs are handed off."""
+    import threading
+    import time
+    from handyrl_b200.train import Trainer
+    from handyrl_b200.nets import tictactoe_net
+    from handyrl_b200.wire import pack_episode
+    with open(os.path.join(GOLDEN, 'batch_cases.pkl'), 'rb') as f:
+        case = pickle.load(f)['tictactoe']
+    flat = [pack_episode(ep, drop_moments=True) for ep in case['episodes']]
+    assert all(ep['moment'] == [] and 'flat' in ep for ep in flat)
+    args = dict(case['args'], batch_size=8, minimum_episodes=4, maximum_episodes=12, num_batchers=1, **{'lambda': 0.7}, num_gpus=1,
+                entropy_regularization=0.1, entropy_regularization_decay=0.1, policy_target='UPGO', value_target='VTRACE')
+    tr = Trainer(args, tictactoe_net())
+    tr.episodes.extend(flat[:5])
+    stop = threading.Event()
+
+    def learner_side():
+        i = 0
+        while not stop.is_set():
+            tr.episodes.extend([dict(flat[i % len(flat)])])
+            while len(tr.episodes) > args['maximum_episodes']:
+                tr.episodes.popleft()
+            i += 1
+            time.sleep(0.002)
+
+    th = threading.Thread(target=tr.run, daemon=True)
+    th.start()
+    feeder = threading.Thread(target=learner_side, daemon=True)
+    feeder.start()
+    seen = 0
+    for _ in range(4):
+        model, steps = tr.update()
+        assert steps > seen and all(torch.isfinite(p).all() for p in model.parameters())
+        seen = steps
+    assert len(tr.gpu_batcher.replay) <= args['maximum_episodes'] and tr.gpu_batcher.fed > 5
+    stop.set()
+    feeder.join(timeout=5)
     tr.stop()
     th.join(timeout=10)
     assert not th.is_alive()
