@@ -11,13 +11,22 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libhrl_b200.so')
 
-HRL_ABI_VERSION = 1
+HRL_ABI_VERSION = 2
 ALGO_ID = {'MC': 0, 'TD': 1, 'UPGO': 2, 'VTRACE': 3}
 LOSS_KEYS = ('p', 'v', 'r', 'ent', 'total', 'dcnt')
 NUM_LOSS = 6
 
 _f32p = C.POINTER(C.c_float)
 _i64p = C.POINTER(C.c_int64)
+
+
+class HrlLossTuning(C.Structure):
+    _fields_ = [('variant', C.c_int32), ('recurrence', C.c_int32), ('cluster', C.c_int32), ('consumers', C.c_int32),
+                ('threads', C.c_int32), ('unstaged', C.c_int32), ('trace', C.c_void_p)]
+
+
+LOSS_VARIANTS = {'auto': 0, 'rows-direct': 1, 'rows-staged': 2, 'bulk': 3, 'element': 4, 'group': 5}
+LOSS_RECURRENCES = {'auto': 0, 'serial': 1, 'scan': 2}
 
 
 class HrlLossArgs(C.Structure):
@@ -37,6 +46,7 @@ class HrlLossArgs(C.Structure):
         ('tap_target_value', C.c_void_p), ('tap_target_return', C.c_void_p), ('tap_advantage', C.c_void_p),
         ('tap_logp', C.c_void_p), ('tap_rho', C.c_void_p), ('tap_entropy', C.c_void_p),
         ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+        ('tuning', HrlLossTuning),
     ]
 
 
@@ -72,7 +82,7 @@ SYMBOLS = {
     'hrl_clip_adam_step': (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 3 +
                            [C.c_double] * 5 + [C.c_void_p, C.c_void_p]),
     'hrl_peer_allreduce_sumsq': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
-                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'hrl_bn_workspace_floats': (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     'hrl_bn_train_fwd': (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     'hrl_bn_train_bwd': (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -772,11 +772,6 @@ static int pow2_ceil(int x) {
     return p;
 }
 
-static int env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
 }  // namespace hrl
 
 extern "C" size_t hrl_loss_workspace_bytes(int32_t B, int32_t, int32_t, int32_t, int32_t) {
@@ -809,9 +804,12 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     prm.has_v = a.value_raw != nullptr;
     prm.has_r = a.return_raw != nullptr;
     prm.cluster = 1;
-    prm.scan = env_int("HRL_LOSS_SCAN", prm.Tt >= 96 ? 1 : 0);   // serial recurrences win below ~100 steps
-    prm.trace = nullptr;
-    if (const char *e = getenv("HRL_LOSS_TRACE")) prm.trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
+    const HrlLossTuning &tune = a.tuning;
+    HRL_REQUIRE(tune.variant >= 0 && tune.variant <= 5 && tune.recurrence >= 0 && tune.recurrence <= 2 && tune.cluster >= 0 &&
+                    tune.cluster <= 8 && tune.consumers >= 0 && tune.threads >= 0 && tune.threads <= 1024 && tune.threads % 32 == 0,
+                HRL_ERR_BAD_ARG, "hrl_loss_fwd_bwd: bad tuning block (zero-initialise HrlLossArgs.tuning for the defaults)");
+    prm.scan = tune.recurrence ? tune.recurrence - 1 : (prm.Tt >= 96 ? 1 : 0);   // serial recurrences win below ~100 steps
+    prm.trace = tune.trace;
 
     int dev = 0, max_smem = 0;
     HRL_CUDA_CHECK(cudaGetDevice(&dev));
@@ -826,13 +824,13 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.policy_raw) & 15) == 0) &&
                            ((reinterpret_cast<uintptr_t>(a.action_mask) & 15) == 0) &&
                            ((reinterpret_cast<uintptr_t>(a.dpolicy_raw) & 15) == 0);
-    const int mode = env_int("HRL_LOSS_MODE", -1);   // -1 auto, 0 direct, 1 staged I/O, 2 bulk
+    const int mode = tune.variant - 1;               // -1 auto, 0 direct, 1 staged I/O, 2 bulk, 3 element, 4 group
 
     // ---- bulk (TMA) kernel: wide rows
     if (LPR == 32 && a.A <= 512 && a.A % 4 == 0 && aligned16 && (mode == -1 || mode == 2)) {
         const size_t two_per_sm = 112 * 1024;     // dynamic shared memory that still lets two CTAs share an SM
-        const int force_cs = env_int("HRL_LOSS_CLUSTER", 0);
-        int NCmax = env_int("HRL_LOSS_CONSUMERS", 16);
+        const int force_cs = tune.cluster;
+        int NCmax = tune.consumers ? tune.consumers : 16;
         if (NCmax > 17) NCmax = 17;
         int best_cs = 0;
         size_t best_bytes = 0;
@@ -882,7 +880,7 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
         if (threads > cap) threads = cap;
         if (threads > 1024) threads = 1024;
         if (threads < 64) threads = 64;
-        threads = env_int("HRL_LOSS_THREADS", threads);
+        if (tune.threads) threads = tune.threads;
         const SmemLayout L = make_layout(EPB, prm.Tt, a.P, a.Pa, 1, a.A, 0, -1, false, prm.scan + 1);
         if ((size_t)L.total * 4 <= (size_t)100 * 1024) {
             prm.EPB = EPB;
@@ -916,7 +914,7 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
         if (threads > cap) threads = cap;
         if (threads > 1024) threads = 1024;
         if (threads < 64) threads = 64;
-        threads = env_int("HRL_LOSS_THREADS", threads);
+        if (tune.threads) threads = tune.threads;
         const SmemLayout L = make_layout(EPB, prm.Tt, a.P, a.Pa, 1, a.A, EPB * per_ep, -1, false, prm.scan + 1);
         if ((size_t)L.total * 4 <= (size_t)100 * 1024) {
             prm.EPB = EPB;
@@ -941,7 +939,7 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
         EPB = (int)(64 / lanes);
         if (EPB > a.B) EPB = a.B;
     }
-    threads = env_int("HRL_LOSS_THREADS", threads);
+    if (tune.threads) threads = tune.threads;
     prm.EPB = EPB;
     const int grid = (a.B + EPB - 1) / EPB;
     const bool vec = (LPR == 32) && (a.A % 4 == 0) && aligned16;
@@ -951,7 +949,7 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     // staging through cp.async pays for narrow rows; from 16 lanes per row on (A > 128) direct coalesced loads and
     // stores are faster (Geister shape, A=214: 35 us direct vs 41 us staged)
     bool ios = !vec && ((mode == -1 && LPR < 16) || mode == 1);
-    prm.stage_z = env_int("HRL_LOSS_STAGE", 1);
+    prm.stage_z = tune.unstaged ? 0 : 1;
     SmemLayout L = make_layout(EPB, prm.Tt, a.P, a.Pa, 1, prm.row_stride, (int)io_floats, -1, false, prm.scan + 1);
     if (ios && (size_t)L.total * 4 > (mode == 1 ? smem_cap : (size_t)100 * 1024)) ios = false;
     if (ios) {

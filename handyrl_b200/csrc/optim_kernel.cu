@@ -96,10 +96,30 @@ __device__ __forceinline__ float4 ld_peer_f4(const float *p) {   // never served
 }
 
 constexpr int kMaxWorld = 16;
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;   // a rank that never arrives must not hang the GPU
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// spin until *flag >= e; gives up after kPeerTimeoutNs (or at once when another wait already gave up) and raises *status
+__device__ __forceinline__ void wait_flag(const uint32_t *flag, uint32_t e, uint32_t *status) {
+    if (ld_acquire_sys(flag) >= e) return;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(flag) < e) {
+        if (*reinterpret_cast<volatile uint32_t *>(status) != 0u) return;
+        if (global_ns() - t0 > kPeerTimeoutNs) {
+            atomicExch(status, 1u);
+            return;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kOptThreads) peer_allreduce_sumsq_kernel(
     float *__restrict__ out, const float *const *__restrict__ peers, int64_t flag_offset, int world, int rank, int64_t n,
-    int64_t n_norm, float *__restrict__ partials, uint32_t *epoch_p, uint32_t *ticket_p) {
+    int64_t n_norm, float *__restrict__ partials, uint32_t *epoch_p, uint32_t *ticket_p, uint32_t *status) {
     __shared__ const float *s_peer[kMaxWorld];
     __shared__ uint32_t s_epoch;
     if (threadIdx.x < world) s_peer[threadIdx.x] = peers[threadIdx.x];
@@ -112,7 +132,7 @@ __global__ void __launch_bounds__(kOptThreads) peer_allreduce_sumsq_kernel(
             for (int p = 0; p < world; p++)
                 st_release_sys(reinterpret_cast<uint32_t *>(const_cast<float *>(s_peer[p])) + flag_offset + rank, e);
         for (int p = 0; p < world; p++)         // wait until every rank's gradients are ready (epochs only grow)
-            while (ld_acquire_sys(my_flags + p) < e) {}
+            wait_flag(my_flags + p, e, status);
     }
     __syncthreads();
 
@@ -142,7 +162,7 @@ __global__ void __launch_bounds__(kOptThreads) peer_allreduce_sumsq_kernel(
             for (int p = 0; p < world; p++)                  // "I am done reading" -> slot [world + rank]
                 st_release_sys(reinterpret_cast<uint32_t *>(const_cast<float *>(s_peer[p])) + flag_offset + world + rank, e);
             for (int p = 0; p < world; p++)                  // nobody still reads MY bucket -> the next step may overwrite it
-                while (ld_acquire_sys(my_flags + world + p) < e) {}
+                wait_flag(my_flags + world + p, e, status);
             *epoch_p = e;
         }
     }
@@ -158,15 +178,15 @@ extern "C" int32_t hrl_sumsq_num_partials(void) { return hrl::kPartials; }
 
 extern "C" int hrl_peer_allreduce_sumsq(float *out_sum, const float *const *peer_buckets, int64_t flag_offset, int32_t world,
                                         int32_t rank, int64_t n, int64_t n_norm, float *partials, uint32_t *epoch, uint32_t *ticket,
-                                        void *stream) {
+                                        uint32_t *status, void *stream) {
     using namespace hrl;
-    HRL_REQUIRE(out_sum && peer_buckets && partials && epoch && ticket, HRL_ERR_BAD_ARG, "hrl_peer_allreduce_sumsq: NULL pointer");
+    HRL_REQUIRE(out_sum && peer_buckets && partials && epoch && ticket && status, HRL_ERR_BAD_ARG, "hrl_peer_allreduce_sumsq: NULL pointer");
     HRL_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, HRL_ERR_BAD_ARG,
                 "hrl_peer_allreduce_sumsq: bad world/rank (%d/%d)", world, rank);
     HRL_REQUIRE(n > 0 && (n & 3) == 0 && (n_norm & 3) == 0 && n_norm <= n && flag_offset >= n, HRL_ERR_BAD_ARG, "hrl_peer_allreduce_sumsq: n must be a positive multiple of 4 and the flags must follow the data");
     // the whole grid must be co-resident (blocks spin on peer flags): 296 blocks x 256 threads always are on B200
     peer_allreduce_sumsq_kernel<<<kPartials, kOptThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        out_sum, peer_buckets, flag_offset, world, rank, n, n_norm, partials, epoch, ticket);
+        out_sum, peer_buckets, flag_offset, world, rank, n, n_norm, partials, epoch, ticket, status);
     HRL_CUDA_CHECK(cudaGetLastError());
     return HRL_OK;
 }

@@ -61,13 +61,16 @@ class LossBuffers:
         self.workspace = torch.zeros(lib().hrl_loss_workspace_bytes(B, T, P, Pa, A), dtype=torch.uint8, device=device)
 
 
-def loss_fwd_bwd(outputs, batch, args, buffers=None, taps=False):
+def loss_fwd_bwd(outputs, batch, args, buffers=None, taps=False, tuning=None):
     """Fused mask epilogue + compute_loss + closed-form backward (reference train.py:176-267).
 
     outputs: raw net outputs {'policy': (B,T,Pa,A), 'value': (B,T,Pa,1)?, 'return': (B,T,Pa,1)?}
     batch:   the make_batch dict (device tensors)
     args:    train_args (lambda, gamma, entropy_regularization[_decay], policy_target, value_target,
              turn_based_training, burn_in_steps)
+    tuning:  None (the library chooses), or a dict for tests / profiling with any of
+             variant ('rows-direct'|'rows-staged'|'bulk'|'element'|'group'), recurrence ('serial'|'scan'),
+             cluster, consumers, threads, unstaged, trace (an int64 CUDA tensor of >= 32 elements)
     returns  LossBuffers with .losses = [p, v, r, ent, total, dcnt] and the gradients.
     """
     policy = _dev_f32(outputs['policy'], 'policy')
@@ -83,7 +86,9 @@ def loss_fwd_bwd(outputs, batch, args, buffers=None, taps=False):
     key = (policy.data_ptr(), 0 if value is None else value.data_ptr(), 0 if ret_head is None else ret_head.data_ptr(),
            args['value_target'], args['policy_target'], bool(args['turn_based_training']), args.get('burn_in_steps', 0),
            args['lambda'], args['gamma'], args['entropy_regularization'], args['entropy_regularization_decay'],
-           buffers.taps is not None) + tuple(batch[k].data_ptr() for k in _BATCH_KEYS)
+           buffers.taps is not None, None if tuning is None else tuple(sorted((k, v if not torch.is_tensor(v) else v.data_ptr())
+                                                                                 for k, v in tuning.items()))) + \
+        tuple(batch[k].data_ptr() for k in _BATCH_KEYS)
     cached = getattr(buffers, '_cached', None)
     if cached is not None and cached[0] == key:
         check(lib().hrl_loss_fwd_bwd(C.byref(cached[1]), _stream_ptr()))
@@ -119,6 +124,18 @@ def loss_fwd_bwd(outputs, batch, args, buffers=None, taps=False):
         a.tap_logp, a.tap_rho, a.tap_entropy = _ptr(t['logp']), _ptr(t['rho']), _ptr(t['entropy'])
     a.workspace = _ptr(buffers.workspace)
     a.workspace_bytes = buffers.workspace.numel()
+    if tuning:
+        t = dict(tuning)
+        a.tuning.variant = _capi.LOSS_VARIANTS[t.pop('variant', 'auto')]
+        a.tuning.recurrence = _capi.LOSS_RECURRENCES[t.pop('recurrence', 'auto')]
+        trace = t.pop('trace', None)
+        if trace is not None:
+            assert trace.is_cuda and trace.dtype == torch.int64 and trace.numel() >= 32
+            a.tuning.trace = trace.data_ptr()
+        for k in ('cluster', 'consumers', 'threads', 'unstaged'):
+            setattr(a.tuning, k, int(t.pop(k, 0)))
+        if t:
+            raise ValueError('unknown loss tuning keys: %s' % sorted(t))
     check(lib().hrl_loss_fwd_bwd(C.byref(a), _stream_ptr()))
     buffers._keep = keep  # the launch is asynchronous: keep temporaries alive
     if all(k is None or k is o for k, o in zip(keep[3:], (batch['action_mask'], batch['action'], batch['selected_prob'],
@@ -294,11 +311,18 @@ class PeerAllReduce:
         self.reduced = torch.zeros(numel, dtype=torch.float32, device=self.device)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         return self.storage
+
+    def check(self):
+        """Raise if a rank ever failed to arrive in the in-kernel rendezvous (the kernel gives up after 20 s instead of
+        spinning forever; its sums are then garbage).  Synchronises the current stream."""
+        if int(self.status.item()) != 0:
+            raise _capi.HrlError('hrl_peer_allreduce_sumsq: a peer rank did not arrive within the timeout')
 
     def __call__(self, n_norm, partials):
         """Enqueue the fused reduce on the current stream; returns the reduced bucket."""
         check(lib().hrl_peer_allreduce_sumsq(_ptr(self.reduced), _ptr(self.peer_ptrs), self.numel, self.world, self.rank,
                                              self.numel, n_norm, _ptr(partials), _ptr(self.epoch), _ptr(self.ticket),
-                                             _stream_ptr()))
+                                             _ptr(self.status), _stream_ptr()))
         return self.reduced

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define HRL_ABI_VERSION 1
+#define HRL_ABI_VERSION 2
 
 typedef enum {
     HRL_OK = 0,
@@ -63,6 +63,20 @@ enum { HRL_LOSS_P = 0, HRL_LOSS_V = 1, HRL_LOSS_R = 2, HRL_LOSS_ENT = 3, HRL_LOS
  * A actions (A <= 1024 and P <= 64 are built; larger values return HRL_ERR_UNSUPPORTED).  Steps t < burn_in are
  * excluded from every loss term and receive zero gradients (train.py:220-222).
  */
+/* Kernel selection and tuning of hrl_loss_fwd_bwd.  All zero = the library's own choice (what production uses);
+ * the fields exist so that tests and profiling can force every code path WITHOUT process-global state (the library
+ * reads no environment variables). */
+typedef struct HrlLossTuning {
+    int32_t variant;     /* 0 auto | 1 rows, direct loads | 2 rows, cp.async-staged | 3 bulk (TMA, wide rows) |
+                            4 element-parallel | 5 lane-group (A <= 32); inapplicable variants fall back to rows */
+    int32_t recurrence;  /* 0 auto (serial below 96 steps) | 1 serial loops | 2 parallel suffix scan           */
+    int32_t cluster;     /* bulk kernel: CTAs per window, 0 auto | 1 | 2 | 4 | 8                               */
+    int32_t consumers;   /* bulk kernel: row-reducing warps per CTA, 0 = 16                                    */
+    int32_t threads;     /* threads per CTA for the other variants, 0 auto                                     */
+    int32_t unstaged;    /* rows kernel: 1 = recompute masked logits instead of staging them in shared memory  */
+    long long *trace;    /* device buffer of >= 32 clock64 stamps written by CTA 0 (debugging), or NULL        */
+} HrlLossTuning;
+
 typedef struct HrlLossArgs {
     int32_t B, T, P, Pa, A;
     int32_t burn_in;
@@ -109,6 +123,7 @@ typedef struct HrlLossArgs {
                                     its first 64 bytes must be zero on the first call and are
                                     left zero by every call                                  */
     size_t workspace_bytes;
+    HrlLossTuning tuning;        /* zero-initialise for the defaults                         */
 } HrlLossArgs;
 
 /* Bytes of workspace hrl_loss_fwd_bwd needs for these dimensions (host call, no GPU work). */
@@ -161,12 +176,14 @@ int hrl_clip_adam_step(float *param, const float *grad, float *exp_avg, float *e
  *   n, n_norm     floats to reduce; the first n_norm of them (the gradients proper, not the loss sums riding in
  *                 the tail) enter the sum of squares
  *   epoch, ticket device uint32, zero-initialised once; maintained by the kernel (CUDA-graph safe)
+ *   status        device uint32, zero-initialised once; set to 1 (and left there) if a peer rank did not arrive
+ *                 within 20 s -- the kernel then gives up instead of spinning forever and its sums are invalid
  * Ranks synchronise inside the kernel with release/acquire flags at system scope: "my gradients are ready"
  * before the loads, "I am done reading" after them, so the next step may overwrite the bucket.
  */
 int hrl_peer_allreduce_sumsq(float *out_sum, const float *const *peer_buckets, int64_t flag_offset, int32_t world,
                              int32_t rank, int64_t n, int64_t n_norm, float *partials, uint32_t *epoch, uint32_t *ticket,
-                             void *stream);
+                             uint32_t *status, void *stream);
 
 /*
  * Train-mode BatchNorm over (N, C, HW) fp32 activations with small HW -- used by the small-board rewrite of the user's

@@ -19,8 +19,9 @@ b = {k: v.cuda() for k, v in b.items()}
 buf = ops.LossBuffers(B, T, P, b['action_mask'].shape[2], A, True, False, 'cuda')
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
 trace = torch.zeros(32, dtype=torch.int64, device='cuda')
-if os.environ.get('TRACE'):
-    os.environ['HRL_LOSS_TRACE'] = str(trace.data_ptr())
+tuning = {'trace': trace} if os.environ.get('TRACE') else None
+if os.environ.get('VARIANT'):
+    tuning = dict(tuning or {}, variant=os.environ['VARIANT'])
 mode = os.environ.get('FLUSH', 'read')
 flush.fill_(1)
 torch.cuda.synchronize()
@@ -29,7 +30,7 @@ for _ in range(reps):
         flush.fill_(1)          # evict L2 with dirty lines (their write-back lands inside the next kernel)
     elif mode == 'read':
         flush.view(torch.int32).sum()   # evict L2 with clean lines
-    ops.loss_fwd_bwd(o, b, args, buffers=buf)
+    ops.loss_fwd_bwd(o, b, args, buffers=buf, tuning=tuning)
 torch.cuda.synchronize()
 print(name, buf.losses.tolist())
 if os.environ.get('TRACE'):

@@ -159,16 +159,15 @@ def test_bad_arguments_fail_loudly():
                          dict(args, burn_in_steps=6))
 
 
-@pytest.mark.parametrize('scan', ['0', '1'], ids=['serial', 'scan'])
+@pytest.mark.parametrize('scan', ['serial', 'scan'])
 @pytest.mark.parametrize('name', ['alt_UPGO_VTRACE', 'sim_TD_UPGO', 'obs_VTRACE_TD', 'alt_MC_UPGO', 'long', 'burnin_alt', 'alt4', 'wide512'])
-def test_both_recurrence_forms_match_reference(name, scan, monkeypatch):
+def test_both_recurrence_forms_match_reference(name, scan):
     """The serial per-column loops (default for short windows) and the parallel suffix scan of max-affine maps
     (default for T >= 96) must both reproduce the reference."""
     from handyrl_b200 import ops
-    monkeypatch.setenv('HRL_LOSS_SCAN', scan)
     case = LOSS_CASES[name]
     batch, outs, grads, losses = split(case)
-    res = ops.loss_fwd_bwd(to_dev(outs), to_dev(batch), case_args(case['meta']))
+    res = ops.loss_fwd_bwd(to_dev(outs), to_dev(batch), case_args(case['meta']), tuning={'recurrence': scan})
     torch.cuda.synchronize()
     got = dict(zip(ops.LOSS_KEYS, res.losses.cpu().tolist()))
     for k, ref in losses.items():
@@ -183,16 +182,15 @@ def test_both_recurrence_forms_match_reference(name, scan, monkeypatch):
 MODE_CASES = ['alt_UPGO_VTRACE', 'obs_TD_TD', 'geese4', 'wide', 'wide512', 'odd33', 'burnin_obs', 'novalue_ret', 'solo1']
 
 
-@pytest.mark.parametrize('mode', ['0', '1', '2', '3', '4'], ids=['rows-direct', 'rows-staged', 'bulk', 'element', 'group'])
+@pytest.mark.parametrize('mode', ['rows-direct', 'rows-staged', 'bulk', 'element', 'group'])
 @pytest.mark.parametrize('name', MODE_CASES)
-def test_every_kernel_variant_matches_reference(name, mode, monkeypatch):
-    """HRL_LOSS_MODE forces one data-movement variant of the fused kernel (falling back to the direct rows kernel
+def test_every_kernel_variant_matches_reference(name, mode):
+    """HrlLossArgs.tuning.variant forces one data-movement variant of the fused kernel (falling back to the direct rows kernel
     where a variant does not apply to the shape): all of them must reproduce the reference."""
     from handyrl_b200 import ops
-    monkeypatch.setenv('HRL_LOSS_MODE', mode)
     case = LOSS_CASES[name]
     batch, outs, grads, losses = split(case)
-    res = ops.loss_fwd_bwd(to_dev(outs), to_dev(batch), case_args(case['meta']))
+    res = ops.loss_fwd_bwd(to_dev(outs), to_dev(batch), case_args(case['meta']), tuning={'variant': mode})
     torch.cuda.synchronize()
     got = dict(zip(ops.LOSS_KEYS, res.losses.cpu().tolist()))
     for k, ref in losses.items():
@@ -204,7 +202,7 @@ def test_every_kernel_variant_matches_reference(name, mode, monkeypatch):
         np.testing.assert_allclose(res.dreturn.cpu().numpy(), grads['return'], rtol=0, atol=ATOL)
 
 
-def test_wide_rows_without_staging_and_cluster_forms(monkeypatch):
+def test_wide_rows_without_staging_and_cluster_forms():
     """Full-size wide-row shape through the non-default forms: 1-CTA bulk, rows-direct with and without z staging."""
     from handyrl_b200 import ops
     from handyrl_b200.synthetic import synthetic_batch, synthetic_outputs
@@ -215,13 +213,9 @@ def test_wide_rows_without_staging_and_cluster_forms(monkeypatch):
     db, do = {k: v.cuda() for k, v in batch.items()}, {k: v.cuda() for k, v in outs.items()}
     ref = ops.loss_fwd_bwd(do, db, args)            # default: 2-CTA cluster bulk kernel (checked against the oracle elsewhere)
     torch.cuda.synchronize()
-    for env in ({'HRL_LOSS_CLUSTER': '1'}, {'HRL_LOSS_MODE': '0'}, {'HRL_LOSS_MODE': '0', 'HRL_LOSS_STAGE': '0'}):
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        res = ops.loss_fwd_bwd(do, db, args)
+    for tuning in ({'cluster': 1}, {'variant': 'rows-direct'}, {'variant': 'rows-direct', 'unstaged': 1}):
+        res = ops.loss_fwd_bwd(do, db, args, tuning=tuning)
         torch.cuda.synchronize()
-        for k in env:
-            monkeypatch.delenv(k)
         np.testing.assert_allclose(res.losses.cpu().numpy(), ref.losses.cpu().numpy(), rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(res.dpolicy.cpu().numpy(), ref.dpolicy.cpu().numpy(), rtol=0, atol=2e-6)
         np.testing.assert_allclose(res.dvalue.cpu().numpy(), ref.dvalue.cpu().numpy(), rtol=0, atol=2e-6)

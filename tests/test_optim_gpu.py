@@ -57,7 +57,7 @@ def test_lr_is_read_from_device():
 def test_peer_allreduce_kernel_world1_matches_sumsq():
     """hrl_peer_allreduce_sumsq with a single rank: the flag protocol must not dead-lock, the reduced bucket equals
     the input, the partials equal hrl_grad_sumsq's over the first n_norm floats, and repeated calls keep working
-    (epochs advance).  The multi-rank form is exercised by scripts/dist_smoke.py and bench.py --gpus N."""
+    (epochs advance).  The multi-rank form: tests/test_multi_gpu.py (world >= 2) and bench.py --gpus N."""
     import ctypes as C
     from handyrl_b200 import ops
     from handyrl_b200._capi import lib, check
@@ -69,14 +69,15 @@ def test_peer_allreduce_kernel_world1_matches_sumsq():
     partials, ref_partials = torch.zeros(npart, device='cuda'), torch.zeros(npart, device='cuda')
     epoch = torch.zeros(1, dtype=torch.int32, device='cuda')
     ticket = torch.zeros(1, dtype=torch.int32, device='cuda')
+    status = torch.zeros(1, dtype=torch.int32, device='cuda')
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     p = lambda t: C.c_void_p(t.data_ptr())
     for it in range(3):
         bucket[:n].normal_()
-        check(lib().hrl_peer_allreduce_sumsq(p(out), p(peer_ptrs), n, world, 0, n, n_norm, p(partials), p(epoch), p(ticket), stream))
+        check(lib().hrl_peer_allreduce_sumsq(p(out), p(peer_ptrs), n, world, 0, n, n_norm, p(partials), p(epoch), p(ticket), p(status), stream))
         torch.cuda.synchronize()
         assert torch.equal(out, bucket[:n])
-        assert int(epoch) == it + 1 and int(ticket) == 0
+        assert int(epoch) == it + 1 and int(ticket) == 0 and int(status) == 0
         want = float((bucket[:n_norm].double() ** 2).sum())
         assert abs(float(partials.double().sum()) - want) <= 1e-5 * want
 
