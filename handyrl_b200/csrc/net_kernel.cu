@@ -1,0 +1,247 @@
+// Elementwise / re-indexing kernels around the user's net on small boards (SURVEY.md 8 f-3 and the small-board rewrite):
+//
+//   hrl_board_expand / hrl_board_fold   conv weight (Cout,Cin,kh,kw) <-> the dense matrix (Cout*HW, Cin*HW) of a stride-1
+//                                       "same" convolution over an H x W board (fastnet.BoardConv2d), and its adjoint
+//   hrl_lstm_gates_fwd / _bwd           the gate arithmetic of a convolutional LSTM cell (reference geister.py:49-56):
+//                                       (i, f, o, g) = split(conv output); c' = sig(f) c + sig(i) tanh(g); h' = sig(o) tanh(c')
+//   hrl_hidden_visible_fwd / _bwd       the hidden state a recurrent net sees at step t (reference train.py:152-158):
+//                                       h * observation_mask, summed over players in the turn-alternating layout
+//   hrl_hidden_blend_fwd / _bwd         the hidden state kept after step t (train.py:173): h (1 - m) + h_new m
+//
+// All are single-pass, coalesced, fp32, one launch each (the eager PyTorch forms are 6-15 launches with temporaries;
+// a Geister learner step runs them ~3,000 times, which is what made that step launch-bound).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace hrl {
+
+// ---- dense <-> conv weight ----------------------------------------------------------------------------------------
+__global__ void board_expand_kernel(const float *__restrict__ w, float *__restrict__ dense, int Cout, int Cin, int kh, int kw, int H,
+                                    int W) {
+    const int HW = H * W;
+    const long long n = (long long)Cout * HW * Cin * HW;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(idx % (Cin * HW)), row = (int)(idx / (Cin * HW));
+        const int o = row / HW, q = row - o * HW, i = col / HW, p = col - i * HW;
+        const int a = p / W - q / W + kh / 2, b = p % W - q % W + kw / 2;       // tap that makes output cell q read input cell p
+        dense[idx] = (a >= 0 && a < kh && b >= 0 && b < kw) ? __ldg(w + ((long long)(o * Cin + i) * kh + a) * kw + b) : 0.f;
+    }
+}
+
+__global__ void board_fold_kernel(const float *__restrict__ ddense, float *__restrict__ dw, int Cout, int Cin, int kh, int kw, int H,
+                                  int W) {
+    const int HW = H * W;
+    const int n = Cout * Cin * kh * kw;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int b = idx % kw, a = (idx / kw) % kh, i = (idx / (kw * kh)) % Cin, o = idx / (kw * kh * Cin);
+        float s = 0.f;
+        for (int qy = 0; qy < H; qy++) {
+            const int py = qy + a - kh / 2;
+            if (py < 0 || py >= H) continue;
+            for (int qx = 0; qx < W; qx++) {
+                const int px = qx + b - kw / 2;
+                if (px < 0 || px >= W) continue;
+                s += __ldg(ddense + (long long)(o * HW + qy * W + qx) * (Cin * HW) + i * HW + py * W + px);
+            }
+        }
+        dw[idx] = s;
+    }
+}
+
+// ---- ConvLSTM gates ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+// gates (N, 4C, S) in the order i, f, o, g; c_prev, h_out, c_out (N, C, S)
+__global__ void lstm_gates_fwd_kernel(const float *__restrict__ gates, const float *__restrict__ c_prev, float *__restrict__ h_out,
+                                      float *__restrict__ c_out, long long N, int CS) {
+    const long long n = N * CS;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / CS;
+        const int r = (int)(idx - b * CS);
+        const float *g = gates + b * 4 * CS + r;
+        const float i = sigmoid_f(__ldg(g)), f = sigmoid_f(__ldg(g + CS)), o = sigmoid_f(__ldg(g + 2 * CS)), gg = tanhf(__ldg(g + 3 * CS));
+        const float c = f * __ldg(c_prev + idx) + i * gg;
+        c_out[idx] = c;
+        h_out[idx] = o * tanhf(c);
+    }
+}
+
+// dh, dc_out may be NULL (= 0); writes dgates (N, 4C, S) and dc_prev (N, C, S)
+__global__ void lstm_gates_bwd_kernel(const float *__restrict__ gates, const float *__restrict__ c_prev, const float *__restrict__ dh,
+                                      const float *__restrict__ dc_out, float *__restrict__ dgates, float *__restrict__ dc_prev,
+                                      long long N, int CS) {
+    const long long n = N * CS;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / CS;
+        const int r = (int)(idx - b * CS);
+        const float *g = gates + b * 4 * CS + r;
+        const float i = sigmoid_f(__ldg(g)), f = sigmoid_f(__ldg(g + CS)), o = sigmoid_f(__ldg(g + 2 * CS)), gg = tanhf(__ldg(g + 3 * CS));
+        const float cp = __ldg(c_prev + idx);
+        const float tc = tanhf(f * cp + i * gg);
+        const float gh = dh ? __ldg(dh + idx) : 0.f;
+        const float dc = (dc_out ? __ldg(dc_out + idx) : 0.f) + gh * o * (1.f - tc * tc);
+        float *dg = dgates + b * 4 * CS + r;
+        dg[0] = dc * gg * i * (1.f - i);
+        dg[CS] = dc * cp * f * (1.f - f);
+        dg[2 * CS] = gh * tc * o * (1.f - o);
+        dg[3 * CS] = dc * i * (1.f - gg * gg);
+        dc_prev[idx] = dc * f;
+    }
+}
+
+// ---- hidden state masking (B, P, R) with the step's observation mask om[b*om_stride + p] -------------------------
+// sum_players = 1: out (B, R) = sum_p h[b,p,:] om[b,p]   (turn-alternating batches: only the turn player observes)
+// sum_players = 0: out (B, P, R) = h om
+__global__ void hidden_visible_fwd_kernel(const float *__restrict__ h, const float *__restrict__ om, long long om_stride,
+                                          float *__restrict__ out, long long B, int P, int R, int sum_players) {
+    const long long n = sum_players ? B * R : B * P * R;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        if (sum_players) {
+            const long long b = idx / R;
+            const int r = (int)(idx - b * R);
+            float s = 0.f;
+            for (int p = 0; p < P; p++) s += __ldg(h + (b * P + p) * R + r) * __ldg(om + b * om_stride + p);
+            out[idx] = s;
+        } else {
+            const long long bp = idx / R;
+            out[idx] = __ldg(h + idx) * __ldg(om + (bp / P) * om_stride + (bp % P));
+        }
+    }
+}
+
+__global__ void hidden_visible_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ om, long long om_stride,
+                                          float *__restrict__ dh, long long B, int P, int R, int sum_players) {
+    const long long n = B * P * R;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const long long bp = idx / R;
+        const int r = (int)(idx - bp * R);
+        const long long b = bp / P;
+        const float m = __ldg(om + b * om_stride + (bp % P));
+        dh[idx] = m * __ldg(dout + (sum_players ? b * R + r : idx));
+    }
+}
+
+// out (B, P, R) = h (1 - m) + nh m, nh is (B, Pn, R) with Pn == P or Pn == 1 (broadcast over players)
+__global__ void hidden_blend_fwd_kernel(const float *__restrict__ h, const float *__restrict__ nh, const float *__restrict__ om,
+                                        long long om_stride, float *__restrict__ out, long long B, int P, int Pn, int R) {
+    const long long n = B * P * R;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const long long bp = idx / R;
+        const int r = (int)(idx - bp * R);
+        const long long b = bp / P;
+        const float m = __ldg(om + b * om_stride + (bp % P));
+        const float v = __ldg(nh + (Pn == 1 ? b * R + r : idx));
+        out[idx] = __ldg(h + idx) * (1.f - m) + v * m;
+    }
+}
+
+// dh (B, P, R) = dout (1 - m); dnh (B, Pn, R) = dout m (summed over players when Pn == 1); dh may be NULL
+__global__ void hidden_blend_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ om, long long om_stride,
+                                        float *__restrict__ dh, float *__restrict__ dnh, long long B, int P, int Pn, int R) {
+    const long long n = (Pn == 1) ? B * R : B * P * R;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        if (Pn == 1) {
+            const long long b = idx / R;
+            const int r = (int)(idx - b * R);
+            float s = 0.f;
+            for (int p = 0; p < P; p++) {
+                const float m = __ldg(om + b * om_stride + p);
+                const float g = __ldg(dout + (b * P + p) * R + r);
+                if (dh) dh[(b * P + p) * R + r] = g * (1.f - m);
+                s += g * m;
+            }
+            dnh[idx] = s;
+        } else {
+            const long long bp = idx / R;
+            const float m = __ldg(om + (bp / P) * om_stride + (bp % P));
+            const float g = __ldg(dout + idx);
+            if (dh) dh[idx] = g * (1.f - m);
+            dnh[idx] = g * m;
+        }
+    }
+}
+
+static inline int grid_for(long long n) {
+    long long b = (n + 255) / 256;
+    const long long cap = (long long)kNumSM * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace hrl
+
+using namespace hrl;
+
+extern "C" int hrl_board_expand(const float *w, float *dense, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W,
+                                void *stream) {
+    HRL_REQUIRE(w && dense && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && H > 0 && W > 0 && (kh & 1) && (kw & 1), HRL_ERR_BAD_ARG,
+                "hrl_board_expand: NULL pointer or bad shape (odd kernels only)");
+    const long long n = (long long)Cout * Cin * H * W * H * W;
+    board_expand_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, dense, Cout, Cin, kh, kw, H, W);
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
+
+extern "C" int hrl_board_fold(const float *ddense, float *dw, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W,
+                              void *stream) {
+    HRL_REQUIRE(ddense && dw && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && H > 0 && W > 0 && (kh & 1) && (kw & 1), HRL_ERR_BAD_ARG,
+                "hrl_board_fold: NULL pointer or bad shape (odd kernels only)");
+    board_fold_kernel<<<grid_for((long long)Cout * Cin * kh * kw), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ddense, dw, Cout, Cin,
+                                                                                                                     kh, kw, H, W);
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
+
+extern "C" int hrl_lstm_gates_fwd(const float *gates, const float *c_prev, float *h_out, float *c_out, int64_t N, int32_t C, int32_t S,
+                                  void *stream) {
+    HRL_REQUIRE(gates && c_prev && h_out && c_out && N > 0 && C > 0 && S > 0, HRL_ERR_BAD_ARG, "hrl_lstm_gates_fwd: NULL pointer or bad shape");
+    lstm_gates_fwd_kernel<<<grid_for(N * C * S), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gates, c_prev, h_out, c_out, N, C * S);
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
+
+extern "C" int hrl_lstm_gates_bwd(const float *gates, const float *c_prev, const float *dh, const float *dc_out, float *dgates,
+                                  float *dc_prev, int64_t N, int32_t C, int32_t S, void *stream) {
+    HRL_REQUIRE(gates && c_prev && dgates && dc_prev && N > 0 && C > 0 && S > 0, HRL_ERR_BAD_ARG, "hrl_lstm_gates_bwd: NULL pointer or bad shape");
+    lstm_gates_bwd_kernel<<<grid_for(N * C * S), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gates, c_prev, dh, dc_out, dgates, dc_prev,
+                                                                                                  N, C * S);
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
+
+extern "C" int hrl_hidden_visible_fwd(const float *h, const float *om, int64_t om_stride, float *out, int64_t B, int32_t P, int32_t R,
+                                      int32_t sum_players, void *stream) {
+    HRL_REQUIRE(h && om && out && B > 0 && P > 0 && R > 0, HRL_ERR_BAD_ARG, "hrl_hidden_visible_fwd: NULL pointer or bad shape");
+    hidden_visible_fwd_kernel<<<grid_for(sum_players ? B * R : B * P * R), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        h, om, om_stride, out, B, P, R, sum_players);
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
+
+extern "C" int hrl_hidden_visible_bwd(const float *dout, const float *om, int64_t om_stride, float *dh, int64_t B, int32_t P, int32_t R,
+                                      int32_t sum_players, void *stream) {
+    HRL_REQUIRE(dout && om && dh && B > 0 && P > 0 && R > 0, HRL_ERR_BAD_ARG, "hrl_hidden_visible_bwd: NULL pointer or bad shape");
+    hidden_visible_bwd_kernel<<<grid_for(B * P * R), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dout, om, om_stride, dh, B, P, R,
+                                                                                                      sum_players);
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
+
+extern "C" int hrl_hidden_blend_fwd(const float *h, const float *nh, const float *om, int64_t om_stride, float *out, int64_t B, int32_t P,
+                                    int32_t Pn, int32_t R, void *stream) {
+    HRL_REQUIRE(h && nh && om && out && B > 0 && P > 0 && R > 0 && (Pn == 1 || Pn == P), HRL_ERR_BAD_ARG,
+                "hrl_hidden_blend_fwd: NULL pointer or bad shape");
+    hidden_blend_fwd_kernel<<<grid_for(B * P * R), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(h, nh, om, om_stride, out, B, P, Pn, R);
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
+
+extern "C" int hrl_hidden_blend_bwd(const float *dout, const float *om, int64_t om_stride, float *dh, float *dnh, int64_t B, int32_t P,
+                                    int32_t Pn, int32_t R, void *stream) {
+    HRL_REQUIRE(dout && om && dnh && B > 0 && P > 0 && R > 0 && (Pn == 1 || Pn == P), HRL_ERR_BAD_ARG,
+                "hrl_hidden_blend_bwd: NULL pointer or bad shape");
+    hidden_blend_bwd_kernel<<<grid_for(Pn == 1 ? B * R : B * P * R), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dout, om, om_stride, dh,
+                                                                                                                      dnh, B, P, Pn, R);
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}

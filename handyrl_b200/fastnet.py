@@ -4,8 +4,11 @@ cuDNN has no efficient kernels for N ~ 10^4, H x W <= ~6x6: on B200 its heuristi
 "grouped direct" kernels that take 0.5-2 ms per layer at N = 16384 (profiles/r01_launches_*), which
 makes the user's net -- not the loss -- 97% of a learner step.  A stride-1 "same" convolution over a
 board with HW cells is exactly a dense linear map (Cin*HW -> Cout*HW) whose matrix is a fixed 0/1
-re-indexing of the kernel weights, so the layer can run as ONE cuBLAS SGEMM on the flattened
-(N, Cin*HW) activations (NCHW-contiguous, no layout change), and BatchNorm2d as two fused reductions.
+re-indexing of the kernel weights, so the layer runs as ONE matrix product per direction on the flattened
+(N, Cin*HW) activations (NCHW-contiguous, no layout change) -- on CUDA through the hand-written tcgen05
+3xTF32 GEMM (csrc/gemm_kernel.cu: tensor cores at fp32-class accuracy; round 1 used cuBLAS SIMT SGEMM, 49% of the
+step) with the dense matrix and its adjoint produced by one kernel each (csrc/net_kernel.cu) -- and BatchNorm2d
+as fused reductions.  ConvLSTM cells (reference geister.py:18-56) get their gate arithmetic fused the same way.
 
 `optimize_small_boards(model)` swaps the class of eligible nn.Conv2d / nn.BatchNorm2d modules in place:
 parameters, buffers and state_dict keys are untouched (reference checkpoints keep loading, workers keep
@@ -16,7 +19,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-MAX_CELLS = 49
+MAX_CELLS = 49            # BatchNorm: fused reductions up to 7x7 boards
+DENSE_MAX_CELLS = 16      # convolution as a dense product: only while the board is about as small as the kernel
+DENSE_MAX_ELEMS = 1 << 20   # ... and the dense matrix stays small (4 MB)
 
 
 def _selection(kh, kw, H, W, ph, pw, device, dtype):
@@ -63,9 +68,13 @@ class _SplitKLinear(torch.autograd.Function):
 class BoardConv2d(nn.Conv2d):
     """nn.Conv2d whose forward runs as a dense GEMM when the board is tiny."""
 
+    dense_calls = 0       # how often the dense path ran (LearnerStep probes this to pick the memory format)
+
     def _eligible(self, x):
         kh, kw = self.kernel_size
-        return (x.dim() == 4 and x.shape[2] * x.shape[3] <= MAX_CELLS and self.stride == (1, 1)
+        cells = x.shape[2] * x.shape[3] if x.dim() == 4 else 0
+        return (x.dim() == 4 and cells <= DENSE_MAX_CELLS
+                and self.out_channels * cells * self.in_channels * cells <= DENSE_MAX_ELEMS and self.stride == (1, 1)
                 and self.dilation == (1, 1) and self.groups == 1 and self.padding_mode == 'zeros'
                 and self.padding == (kh // 2, kw // 2) and kh % 2 == 1 and kw % 2 == 1)
 
@@ -83,6 +92,14 @@ class BoardConv2d(nn.Conv2d):
         N, Cin, H, W = x.shape
         HW = H * W
         Cout = self.out_channels
+        BoardConv2d.dense_calls += 1
+        if x.is_cuda and x.dtype == torch.float32:
+            # tensor cores: dense matrix by one kernel, then forward / input-gradient / weight-gradient as tcgen05 products
+            from . import ops
+            y = ops.linear_tc(x.reshape(N, Cin * HW), ops.board_dense(self.weight, H, W)).reshape(N, Cout, H, W)
+            if self.bias is not None:
+                y = y + self.bias.view(1, Cout, 1, 1)
+            return y
         S = self._sel(H, W, x.device, x.dtype)                                        # (K, HW, HW)
         # dense matrix of the layer: Wb[(o,q),(i,p)] = sum_k w[o,i,k] S[k,q,p]
         Wb = (self.weight.reshape(Cout * Cin, -1) @ S.reshape(S.shape[0], HW * HW))
@@ -104,7 +121,7 @@ class BoardBatchNorm2d(nn.BatchNorm2d):
         N, C, H, W = x.shape
         if self.momentum is None:
             raise NotImplementedError('cumulative moving average BatchNorm is not rewritten')
-        if x.is_cuda and x.dtype == torch.float32 and self.affine:
+        if x.is_cuda and x.dtype == torch.float32 and self.affine and x.is_contiguous():
             # fused kernels (csrc/bn_kernel.cu): 3 coalesced passes forward, 3 backward
             from . import ops
             with torch.no_grad():
@@ -128,6 +145,31 @@ class BoardBatchNorm2d(nn.BatchNorm2d):
 
 _SWAPS = {nn.Conv2d: BoardConv2d, nn.BatchNorm2d: BoardBatchNorm2d}
 _UNSWAPS = {v: k for k, v in _SWAPS.items()}
+_CELL_CLASSES = {}        # original ConvLSTM cell class -> fused subclass
+
+
+def _is_conv_lstm_cell(m):
+    """Duck-typed ConvLSTM cell: one convolution `conv` over [input, h] whose output holds the four gate maps of
+    `hidden_dim` (reference geister.py:18-35) / `state_maps` (nets.ConvLstmCell) channels, called as cell(x, (h, c))."""
+    conv = getattr(m, 'conv', None)
+    maps = getattr(m, 'hidden_dim', None) or getattr(m, 'state_maps', None)
+    return (isinstance(conv, nn.Conv2d) and isinstance(maps, int) and conv.out_channels == 4 * maps
+            and len(list(m.children())) == 1 and not isinstance(m, nn.Conv2d))
+
+
+def _fused_cell_class(cls):
+    if cls not in _CELL_CLASSES:
+        def forward(self, x, state):
+            h, c = state
+            gates = self.conv(torch.cat([x, h], dim=-3))
+            if gates.is_cuda and gates.dtype == torch.float32 and gates.dim() == 4:
+                from . import ops
+                return ops.lstm_gates(gates, c)           # one kernel forward, one backward (csrc/net_kernel.cu)
+            i, f, o, g = gates.chunk(4, dim=-3)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            return torch.sigmoid(o) * torch.tanh(c), c
+        _CELL_CLASSES[cls] = type('Fused' + cls.__name__, (cls,), {'forward': forward, '_hrl_original': cls})
+    return _CELL_CLASSES[cls]
 
 
 def optimize_small_boards(model):
@@ -136,6 +178,9 @@ def optimize_small_boards(model):
     for m in model.modules():
         if type(m) in _SWAPS:
             m.__class__ = _SWAPS[type(m)]
+            n += 1
+        elif _is_conv_lstm_cell(m) and not hasattr(type(m), '_hrl_original'):
+            m.__class__ = _fused_cell_class(type(m))
             n += 1
     return n
 
@@ -146,4 +191,6 @@ def restore(model):
         if type(m) in _UNSWAPS:
             m.__dict__.pop('_sel_cache', None)
             m.__class__ = _UNSWAPS[type(m)]
+        elif hasattr(type(m), '_hrl_original'):
+            m.__class__ = type(m)._hrl_original
     return model

@@ -243,6 +243,172 @@ class FlatAdam:
                                        self.weight_decay, _ptr(self.grad_norm), s))
 
 
+def gemm_tf32x3(a, b, bias=None, a_kmajor=True, b_kmajor=True, splits=1, out=None):
+    """C = A_op @ B_op^T (+ bias) on the tensor cores with fp32-class accuracy (hrl_gemm_tf32x3, csrc/gemm_kernel.cu).
+
+    a: (M, K) if a_kmajor else (K, M) -- the operand as it lies in memory; b likewise (N, K) / (K, N).
+    """
+    assert a.is_cuda and b.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[0], a.shape[1]) if a_kmajor else (a.shape[1], a.shape[0])
+    N, Kb = (b.shape[0], b.shape[1]) if b_kmajor else (b.shape[1], b.shape[0])
+    assert K == Kb, (a.shape, b.shape, a_kmajor, b_kmajor)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    ws = None
+    if splits > 1:
+        ws = torch.empty(lib().hrl_gemm_workspace_floats(M, N, K, splits), dtype=torch.float32, device=a.device)
+    check(lib().hrl_gemm_tf32x3(_ptr(a), a.stride(0), int(a_kmajor), _ptr(b), b.stride(0), int(b_kmajor), _ptr(bias), _ptr(out),
+                                out.stride(0), M, N, K, splits, _ptr(ws), _stream_ptr()))
+    return out
+
+
+class _LinearTC(torch.autograd.Function):
+    """y = x @ w^T with all three products (forward, input gradient, weight gradient) on the tensor cores at fp32-class
+    accuracy (hrl_gemm_tf32x3).  The weight gradient reduces over the rows of x (samples): both operands are read
+    transposed on the fly and the reduction is split over enough K slices to fill the GPU."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x, w = x.contiguous(), w.contiguous()
+        ctx.save_for_backward(x, w)
+        return gemm_tf32x3(x, w)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_tf32x3(dy, w, b_kmajor=False)                       # (M,N) x (N,K): w is read as stored
+        if ctx.needs_input_grad[1]:
+            M = x.shape[0]
+            tiles = ((w.shape[0] + 127) // 128) * ((w.shape[1] + 287) // 288)
+            splits = max(1, min(M // 64, 148 // tiles))
+            dw = gemm_tf32x3(dy, x, a_kmajor=False, b_kmajor=False, splits=splits)
+        return dx, dw
+
+
+def linear_tc(x, w):
+    return _LinearTC.apply(x, w)
+
+
+class _BoardDense(torch.autograd.Function):
+    """Dense matrix of a small-board convolution from its weight (hrl_board_expand) and the adjoint (hrl_board_fold)."""
+
+    @staticmethod
+    def forward(ctx, weight, H, W):
+        weight = weight.contiguous()
+        Cout, Cin, kh, kw = weight.shape
+        ctx.dims = (Cout, Cin, kh, kw, H, W)
+        dense = torch.empty((Cout * H * W, Cin * H * W), dtype=torch.float32, device=weight.device)
+        check(lib().hrl_board_expand(_ptr(weight), _ptr(dense), Cout, Cin, kh, kw, H, W, _stream_ptr()))
+        return dense
+
+    @staticmethod
+    def backward(ctx, ddense):
+        Cout, Cin, kh, kw, H, W = ctx.dims
+        ddense = ddense.contiguous()
+        dw = torch.empty((Cout, Cin, kh, kw), dtype=torch.float32, device=ddense.device)
+        check(lib().hrl_board_fold(_ptr(ddense), _ptr(dw), Cout, Cin, kh, kw, H, W, _stream_ptr()))
+        return dw, None, None
+
+
+def board_dense(weight, H, W):
+    return _BoardDense.apply(weight, H, W)
+
+
+class _LstmGates(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gates, c_prev):
+        gates, c_prev = gates.contiguous(), c_prev.contiguous()
+        N, C4 = gates.shape[:2]
+        S = gates[0, 0].numel()
+        h, c = torch.empty_like(c_prev), torch.empty_like(c_prev)
+        check(lib().hrl_lstm_gates_fwd(_ptr(gates), _ptr(c_prev), _ptr(h), _ptr(c), N, C4 // 4, S, _stream_ptr()))
+        ctx.save_for_backward(gates, c_prev)
+        return h, c
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        gates, c_prev = ctx.saved_tensors
+        N, C4 = gates.shape[:2]
+        S = gates[0, 0].numel()
+        dgates, dc_prev = torch.empty_like(gates), torch.empty_like(c_prev)
+        check(lib().hrl_lstm_gates_bwd(_ptr(gates), _ptr(c_prev), _ptr(None if dh is None else dh.contiguous()),
+                                       _ptr(None if dc is None else dc.contiguous()), _ptr(dgates), _ptr(dc_prev), N, C4 // 4, S,
+                                       _stream_ptr()))
+        return dgates, dc_prev
+
+
+def lstm_gates(gates, c_prev):
+    """(h', c') of a convolutional LSTM cell from its gate pre-activations (N,4C,...) in the order i, f, o, g."""
+    return _LstmGates.apply(gates, c_prev)
+
+
+def _mask_view(om):
+    """observation_mask[:, t] (B,P,1) as (pointer tensor, batch stride): element (b,p) at base + b*stride + p."""
+    assert om.dim() == 3 and om.shape[2] == 1 and (om.stride(1) == 1 or om.shape[1] == 1) and om.dtype == torch.float32
+    return om, om.stride(0)
+
+
+class _HiddenVisible(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, om, sum_players):
+        h = h.contiguous()
+        B, P = h.shape[:2]
+        R = h[0, 0].numel()
+        om, stride = _mask_view(om)
+        out = torch.empty((B,) + tuple(h.shape[2:]) if sum_players else h.shape, dtype=torch.float32, device=h.device)
+        check(lib().hrl_hidden_visible_fwd(_ptr(h), _ptr(om), stride, _ptr(out), B, P, R, int(sum_players), _stream_ptr()))
+        ctx.save_for_backward(om)
+        ctx.meta = (B, P, R, stride, bool(sum_players), tuple(h.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        om, = ctx.saved_tensors
+        B, P, R, stride, sum_players, shape = ctx.meta
+        dh = torch.empty(shape, dtype=torch.float32, device=dout.device)
+        check(lib().hrl_hidden_visible_bwd(_ptr(dout.contiguous()), _ptr(om), stride, _ptr(dh), B, P, R, int(sum_players), _stream_ptr()))
+        return dh, None, None
+
+
+class _HiddenBlend(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, nh, om):
+        h, nh = h.contiguous(), nh.contiguous()
+        B, P = h.shape[:2]
+        Pn = nh.shape[1]
+        R = h[0, 0].numel()
+        om, stride = _mask_view(om)
+        out = torch.empty_like(h)
+        check(lib().hrl_hidden_blend_fwd(_ptr(h), _ptr(nh), _ptr(om), stride, _ptr(out), B, P, Pn, R, _stream_ptr()))
+        ctx.save_for_backward(om)
+        ctx.meta = (B, P, Pn, R, stride, tuple(h.shape), tuple(nh.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        om, = ctx.saved_tensors
+        B, P, Pn, R, stride, hshape, nshape = ctx.meta
+        dh = torch.empty(hshape, dtype=torch.float32, device=dout.device) if ctx.needs_input_grad[0] else None
+        dnh = torch.empty(nshape, dtype=torch.float32, device=dout.device)
+        check(lib().hrl_hidden_blend_bwd(_ptr(dout.contiguous()), _ptr(om), stride, _ptr(dh), _ptr(dnh), B, P, Pn, R, _stream_ptr()))
+        return dh, dnh, None
+
+
+def hidden_visible(h, om, sum_players):
+    """The hidden leaf a recurrent net sees at one step (train.py:152-158): h (B,P,...) masked by om (B,P,1), summed
+    over players when sum_players (turn-alternating batches) -- one kernel instead of mul + sum."""
+    return _HiddenVisible.apply(h, om, sum_players)
+
+
+def hidden_blend(h, nh, om):
+    """h (1 - om) + nh om (train.py:173), nh (B,Pa,...) broadcast over players when Pa == 1 -- one kernel."""
+    return _HiddenBlend.apply(h, nh, om)
+
+
 class _BatchNormTrain(torch.autograd.Function):
     """nn.BatchNorm2d (training mode) on (N, C, H, W) with a small board, through hrl_bn_train_fwd / _bwd."""
 

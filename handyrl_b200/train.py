@@ -70,11 +70,17 @@ def forward_raw(model, hidden, batch, args, memory_format=None):
         def gate(h):
             return om.view(*h.shape[:2], *([1] * (h.dim() - 2)))
 
-        visible = tree_map(lambda h: h * gate(h), hidden)
-        if alternating:
-            visible = tree_map(lambda h: h.sum(1), visible)                    # only the turn player observes
+        fused = om.is_cuda and om.dtype == torch.float32          # one kernel per hidden leaf instead of mul + sum / blend chains
+        if fused:
+            visible = tree_map(lambda h: ops.hidden_visible(h, om, alternating), hidden)
+            if not alternating:
+                visible = tree_map(lambda h: h.flatten(0, 1), visible)
         else:
-            visible = tree_map(lambda h: h.flatten(0, 1), visible)
+            visible = tree_map(lambda h: h * gate(h), hidden)
+            if alternating:
+                visible = tree_map(lambda h: h.sum(1), visible)                # only the turn player observes
+            else:
+                visible = tree_map(lambda h: h.flatten(0, 1), visible)
         if t < burn_in:
             model.eval()
             with torch.no_grad():
@@ -88,7 +94,10 @@ def forward_raw(model, hidden, batch, args, memory_format=None):
             if v is not None:
                 per_step.setdefault(k, []).append(v.unflatten(0, (B, Pa)))
         new_hidden = tree_map(lambda h: h.unflatten(0, (B, Pa)), new_hidden)
-        hidden = tree_map(lambda h, nh: h * (1 - gate(h)) + nh * gate(h), hidden, new_hidden)
+        if fused:
+            hidden = tree_map(lambda h, nh: ops.hidden_blend(h, nh, om), hidden, new_hidden)
+        else:
+            hidden = tree_map(lambda h, nh: h * (1 - gate(h)) + nh * gate(h), hidden, new_hidden)
     return {k: torch.stack(v, dim=1) for k, v in per_step.items()}
 
 
@@ -148,6 +157,10 @@ def compute_loss(batch, model, hidden, args):
 
 
 # --------------------------------------------------------------------------- one learner step
+
+def obs_rows(obs):
+    return tree_leaves(obs)[0].shape[0]
+
 
 def _align(x, a=256):
     return (x + a - 1) // a * a
@@ -340,8 +353,8 @@ class LearnerStep:
         # implicit-GEMM kernels on the tiny boards of these games; NHWC + autotune is a pure layout choice
         # tiny boards: convolutions as one SGEMM, BatchNorm as fused reductions (fastnet.py); NCHW stays as is
         self.rewritten = fastnet.optimize_small_boards(self.model) if small_boards else 0
-        if self.rewritten:
-            channels_last = False
+        if self.rewritten and channels_last:
+            channels_last = not self._uses_dense_convs(example_batch)       # dense products want NCHW-flat activations
         self.memory_format = torch.channels_last if channels_last else None
         if channels_last:
             self.model = self.model.to(memory_format=torch.channels_last)
@@ -390,6 +403,21 @@ class LearnerStep:
         self.steps = 0
         self.stream = torch.cuda.Stream(device=self.device)
         self._warm = PackedBatch(self.layout).fill(example_batch)
+
+    def _uses_dense_convs(self, example_batch):
+        """One no-grad probe call of the net on a two-sample slice: do its convolutions take the dense small-board path
+        (then activations stay NCHW) or cuDNN (then NHWC, whose implicit-GEMM kernels are the fast ones)?"""
+        before = fastnet.BoardConv2d.dense_calls
+        obs = tree_map(lambda o: o[:1, :1].flatten(0, 2).to(self.device), example_batch['observation'])
+        hidden = None
+        if hasattr(self.model, 'init_hidden'):
+            hidden = tree_map(lambda h: h.to(self.device), self.model.init_hidden([obs_rows(obs)]))
+        was_training = self.model.training
+        self.model.eval()
+        with torch.no_grad():
+            self.model(obs, hidden)
+        self.model.train(was_training)
+        return fastnet.BoardConv2d.dense_calls > before
 
     # -- the device work of one step, on the current stream (inputs already in self.dev)
     def _part_forward(self):

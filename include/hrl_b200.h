@@ -16,6 +16,7 @@
  *   hrl_clip_adam_step    <- handyrl/train.py:370-371 (clip_grad_norm_(params, 4.0) + Adam.step,
  *                            Adam(lr, weight_decay=1e-5) of train.py:331)
  *   hrl_gather_pad        <- handyrl/train.py:33-124  (make_batch: window slice + pad + collate)
+ *   hrl_gemm_tf32x3       <- the Linear/Conv contractions of the user's net inside train.py:142-146 (+ autograd, :369)
  *
  * Conventions
  *   - plain C, no torch types; every pointer is a DEVICE pointer unless stated;
@@ -184,6 +185,61 @@ int hrl_clip_adam_step(float *param, const float *grad, float *exp_avg, float *e
 int hrl_peer_allreduce_sumsq(float *out_sum, const float *const *peer_buckets, int64_t flag_offset, int32_t world,
                              int32_t rank, int64_t n, int64_t n_norm, float *partials, uint32_t *epoch, uint32_t *ticket,
                              uint32_t *status, void *stream);
+
+/*
+ * fp32-accurate matrix product on the tensor cores (tcgen05.mma kind::tf32 with the 3xTF32 hi/lo split, fp32
+ * accumulation in tensor memory) -- the dense contractions of the user's net (fastnet.py runs a convolution over a
+ * tiny board as one such product per direction), i.e. what torch.nn.functional.linear / conv2d and their autograd
+ * do inside reference train.py:142-146, 369.
+ *     C[M x N] = A_op[M x K] * B_op[N x K]^T (+ bias[N])
+ *   a_kmajor / b_kmajor  1: element (row, k) of the operand at  row * ld + k  (reduction dimension contiguous)
+ *                        0: at  k * ld + row  (the operand is stored transposed, e.g. reduce over samples)
+ *   splits               K slices computed by separate CTAs into `workspace` (hrl_gemm_workspace_floats floats) and
+ *                        summed in a fixed order (deterministic); 1 = no split, workspace may be NULL.  A split
+ *                        product takes no bias and needs ldc == N.
+ * Relative error ~1e-6 of sum_k |a||b| (plain fp32 summation is ~1e-7 * sqrt(K)); NOT the 1e-3 of single-pass TF32.
+ */
+size_t hrl_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int32_t splits);
+int hrl_gemm_tf32x3(const float *A, int64_t lda, int32_t a_kmajor, const float *B, int64_t ldb, int32_t b_kmajor,
+                    const float *bias, float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t splits,
+                    float *workspace, void *stream);
+
+/*
+ * Weight of a stride-1 "same" convolution (Cout,Cin,kh,kw; odd kernel, zero padding) <-> the dense matrix
+ * (Cout*H*W, Cin*H*W) that applies it to an H x W board stored NCHW (fastnet.BoardConv2d), and the adjoint map
+ * dense-gradient -> weight-gradient.  dense[(o,q),(i,p)] = w[o,i,a,b] where tap (a,b) makes output cell q read input
+ * cell p, 0 if no tap does.
+ */
+int hrl_board_expand(const float *w, float *dense, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W,
+                     void *stream);
+int hrl_board_fold(const float *ddense, float *dw, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W,
+                   void *stream);
+
+/*
+ * Recurrent nets.  ConvLSTM gate arithmetic (reference geister.py:49-56): gates (N,4C,S) in the order
+ * i, f, o, g are the cell's convolution output; c' = sig(f) c + sig(i) tanh(g), h' = sig(o) tanh(c').  The backward
+ * recomputes the activations from `gates` and `c_prev`; dh / dc_out may be NULL (no gradient from that side).
+ */
+int hrl_lstm_gates_fwd(const float *gates, const float *c_prev, float *h_out, float *c_out, int64_t N, int32_t C, int32_t S,
+                       void *stream);
+int hrl_lstm_gates_bwd(const float *gates, const float *c_prev, const float *dh, const float *dc_out, float *dgates,
+                       float *dc_prev, int64_t N, int32_t C, int32_t S, void *stream);
+
+/*
+ * Hidden-state masking of the recurrent time loop (reference train.py:152-158, 173) on a hidden leaf h (B,P,R):
+ *   visible: out = h * om[b,p]            (sum_players = 0, out (B,P,R))
+ *            out = sum_p h * om[b,p]      (sum_players = 1, out (B,R): turn-alternating batches)
+ *   blend:   out = h (1 - om) + h_new om  (h_new (B,Pn,R), Pn == P or 1)
+ * om points at observation_mask[:, t] = element (b,p) at om[b * om_stride + p].
+ */
+int hrl_hidden_visible_fwd(const float *h, const float *om, int64_t om_stride, float *out, int64_t B, int32_t P, int32_t R,
+                           int32_t sum_players, void *stream);
+int hrl_hidden_visible_bwd(const float *dout, const float *om, int64_t om_stride, float *dh, int64_t B, int32_t P, int32_t R,
+                           int32_t sum_players, void *stream);
+int hrl_hidden_blend_fwd(const float *h, const float *nh, const float *om, int64_t om_stride, float *out, int64_t B, int32_t P,
+                         int32_t Pn, int32_t R, void *stream);
+int hrl_hidden_blend_bwd(const float *dout, const float *om, int64_t om_stride, float *dh, float *dnh, int64_t B, int32_t P,
+                         int32_t Pn, int32_t R, void *stream);
 
 /*
  * Train-mode BatchNorm over (N, C, HW) fp32 activations with small HW -- used by the small-board rewrite of the user's
