@@ -1,24 +1,30 @@
 #!/usr/bin/env python
-"""Benchmark of the HandyRL learner hot path on B200 (contract: see the task statement / DESIGN.md).
+"""Benchmark of the HandyRL learner hot path on B200 (contract: see the task statement / DESIGN.md section 6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one learner step on one replay batch: Batcher output -> net forward -> fused loss
-fwd+bwd kernel -> net backward -> [NCCL all-reduce SUM] -> clip + Adam.
+fwd+bwd kernel -> net backward -> [all-reduce SUM] -> clip + Adam.
 metric = learner samples/s = B*T*steps/s over all GPUs (BASELINE.json).
 
-  value     inputs already resident in HBM (a ring of distinct batches larger than L2)
-  e2e       the same step through LearnerStep.step() with HOST (pinned) batches: one H2D copy per
-            step and a D2H read of the step's loss sums inside the timed region
-  roofline  the fused loss kernel: algorithmic bytes / CUDA-event duration measured live in the
-            timed region, against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline / --impl reference: the eager-PyTorch CPU port of the reference learner step
-            (oracle/torch_learner.py, pinned to the reference's golden vectors) on the host cores.
+  value        inputs already resident in HBM (a ring of distinct batches larger than L2)
+  e2e          the same step through LearnerStep.step() with HOST (pinned) batches: one H2D copy per step (on a copy
+               stream, one step ahead of the compute) and a D2H read of the step's loss sums inside the timed region
+  e2e_trainer  (N=1) the whole drop-in Trainer fed by a deque of episodes in the reference's wire format: episode
+               decode + upload by the feeder thread, window sampling, gather/pad kernel, step, epoch hand-offs --
+               the part `e2e` starts after (Batcher.batch, reference train.py:317-318, 358)
+  roofline     the fused loss kernel: algorithmic bytes / CUDA-event duration measured live in the timed region,
+               against the measured HBM copy bandwidth (MEASURED_PEAKS.json); roofline_wide_rows: the same kernel alone
+               at the wide-row shape; roofline_k2: the replay gather/pad kernel alone
+  cpu_baseline / --impl reference: the eager-PyTorch CPU port of the reference learner step (oracle/torch_learner.py,
+               pinned to the reference's golden vectors) on the host cores: ALWAYS the workload's full batch, a fixed
+               thread count, 3+ warm-ups, min / median / mean, loss-only and full step reported separately.
 """
 import argparse
 import json
 import os
+import statistics
 import sys
 import threading
 import time
@@ -29,52 +35,76 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 WORKLOADS = {
+    # BASELINE.json configs[0]: the reference's own config.yaml shape -- TicTacToe episodes, batch_size 64, forward_steps 16,
+    # V-Trace (CPU-runnable case; episodes from handyrl_b200.synthetic.tictactoe_episodes in the reference's wire format)
+    'cfg1': dict(B=64, T=16, P=2, A=9, turn_based=True, observation=False, obs_shape=(3, 3, 3), net='tictactoe',
+                 policy_target='VTRACE', value_target='VTRACE', reward_kind='zero', episodes=True,
+                 desc='configs[0]: TicTacToe net (29,006 params), self-play episodes, batch_size=64 forward_steps=16, V-Trace'),
     # BASELINE.json configs[1]: TicTacToe net, synthetic replay (T=32,B=512,P=2), V-Trace + UPGO
     'cfg2': dict(B=512, T=32, P=2, A=9, turn_based=True, observation=False, obs_shape=(3, 3, 3), net='tictactoe',
                  policy_target='UPGO', value_target='VTRACE', reward_kind='zero',
                  desc='configs[1]: TicTacToe net (29,006 params), synthetic replay T=32 B=512/GPU P=2 Pa=1 A=9, '
                       'policy UPGO + value V-Trace'),
+    # BASELINE.json configs[2]: the Geister architecture (DRC ConvLSTM 3 layers x 3 repeats, 231,604 params; dict observation;
+    # policy/value/return heads), TD(lambda), batch 256, burn-in 4 + 16 forward steps
+    'cfg3': dict(B=256, T=20, P=2, A=214, turn_based=True, observation=True, obs_shape=None, net='geister', burn_in=4,
+                 policy_target='TD', value_target='TD', reward_kind='step',
+                 desc='configs[2]: Geister net (DRC ConvLSTM, 231,604 params, recurrent path), TD(lambda), B=256/GPU, '
+                      'T=4 burn-in + 16, P=Pa=2, A=214, dict observation {scalar 18, board 7x6x6}'),
+    # BASELINE.json configs[3]: Hungry Geese architecture (12-block torus tower, 116,928 params), V-Trace, batch 1024 over 4 GPUs
+    'cfg4': dict(B=256, T=32, P=4, A=4, turn_based=False, observation=False, obs_shape=(17, 7, 11), net='geese',
+                 policy_target='VTRACE', value_target='VTRACE', reward_kind='zero',
+                 desc='configs[3]: Hungry Geese net (torus conv tower, 116,928 params), V-Trace, B=256/GPU (1024 over 4 GPUs), '
+                      'T=32, P=Pa=4, A=4, obs 17x7x11'),
     # per-GPU shard of BASELINE.json configs[4]: 64x64 obs, 512 actions, T=64, B=4096/8
     'cfg5shard': dict(B=512, T=64, P=2, A=512, turn_based=True, observation=False, obs_shape=(1, 64, 64), net='wide',
                       policy_target='UPGO', value_target='VTRACE', reward_kind='zero',
                       desc='configs[4] per-GPU shard: 64x64 obs / 512 actions, T=64 B=512/GPU P=2 Pa=1'),
-    # BASELINE.json configs[2]: Geister-shaped recurrent net (dict observation, policy/value/return heads), TD(lambda),
-    # batch 256, burn-in 4 + 16 forward steps
-    'cfg3': dict(B=256, T=20, P=2, A=214, turn_based=True, observation=True, obs_shape=None, net='geister', burn_in=4,
-                 policy_target='TD', value_target='TD', reward_kind='step',
-                 desc='configs[2]: Geister-shaped recurrent net (conv-gated memory, 3 heads), TD(lambda), B=256/GPU, '
-                      'T=4 burn-in + 16, P=Pa=2, A=214, dict observation {scalar 18, board 7x6x6}'),
 }
 L2_BYTES = 126e6
+CPU_THREADS = max(1, min(64, (os.cpu_count() or 2) // 2))       # fixed: the host's physical cores, at most 64
 
 
 def train_args(w):
     return {'turn_based_training': w['turn_based'], 'observation': w['observation'], 'gamma': 0.8, 'lambda': 0.7,
             'burn_in_steps': w.get('burn_in', 0), 'forward_steps': w['T'] - w.get('burn_in', 0), 'entropy_regularization': 0.1,
             'entropy_regularization_decay': 0.1, 'policy_target': w['policy_target'], 'value_target': w['value_target'],
-            'batch_size': w['B']}
+            'batch_size': w['B'], 'compress_steps': 4, 'maximum_episodes': 100000, 'minimum_episodes': 400, 'num_batchers': 1,
+            'seed': 0}
 
 
 def make_net(w):
     from handyrl_b200 import nets
     torch.manual_seed(0)
-    if w['net'] == 'geister':
-        return nets.GatedBoardNet(scalars=18, planes=7, board=(6, 6), width=32, actions=w['A'])
-    return nets.tictactoe_net() if w['net'] == 'tictactoe' else nets.WideActionNet()
+    return {'tictactoe': nets.tictactoe_net, 'geister': nets.geister_net, 'geese': nets.geese_net, 'wide': nets.WideActionNet}[w['net']]()
 
 
-def make_batch(w, seed, B=None):
-    from handyrl_b200.synthetic import synthetic_batch
+_EPISODES = {}
+
+
+def episodes_for(w, n=2000):
+    from handyrl_b200.synthetic import tictactoe_episodes
+    if n not in _EPISODES:
+        _EPISODES[n] = tictactoe_episodes(n, seed=123)
+    return _EPISODES[n]
+
+
+def make_batch(w, seed):
+    """One replay batch of the workload at its FULL batch size."""
+    from handyrl_b200 import synthetic
+    if w.get('episodes'):           # windows drawn from real episodes by the host batcher (reference sampling law)
+        import random
+        from collections import deque
+        from handyrl_b200.train import Batcher
+        random.seed(seed)
+        return Batcher(train_args(w), deque(episodes_for(w)))._make()
     if w['net'] == 'geister':
-        b = synthetic_batch(B or w['B'], w['T'], w['P'], w['A'], turn_based=w['turn_based'], observation=w['observation'],
-                            reward_kind=w['reward_kind'], seed=seed, burn_in=w.get('burn_in', 0), with_obs=False)
-        g = torch.Generator().manual_seed(seed + 7)
-        Bn, T, Pa = b['action'].shape[:3]
-        b['observation'] = {'scalar': torch.rand((Bn, T, Pa, 18), generator=g),
-                            'board': (torch.rand((Bn, T, Pa, 7, 6, 6), generator=g) < 0.3).float()}
-        return b
-    return synthetic_batch(B or w['B'], w['T'], w['P'], w['A'], turn_based=w['turn_based'], observation=w['observation'],
-                           reward_kind=w['reward_kind'], seed=seed, obs_shape=w['obs_shape'])
+        return synthetic.synthetic_geister_batch(w['B'], w['T'], w['P'], w['A'], turn_based=w['turn_based'], observation=w['observation'],
+                                                 burn_in=w.get('burn_in', 0), seed=seed)
+    if w['net'] == 'geese':
+        return synthetic.synthetic_geese_batch(w['B'], w['T'], w['P'], w['A'], seed=seed)
+    return synthetic.synthetic_batch(w['B'], w['T'], w['P'], w['A'], turn_based=w['turn_based'], observation=w['observation'],
+                                     reward_kind=w['reward_kind'], seed=seed, obs_shape=w['obs_shape'])
 
 
 def measured_peak():
@@ -148,51 +178,71 @@ def physical_device_index(local):
 
 # ------------------------------------------------------------------------------ CPU arm
 
-def run_cpu_port(w, steps, warmup, budget_s, threads=None):
-    """The eager-PyTorch CPU port of the reference learner step on a bounded sample."""
-    from oracle.torch_learner import CpuLearner
-    if threads:
-        torch.set_num_threads(threads)
+def run_cpu_port(w, steps, warmup, threads, loss_only_too=True):
+    """The eager-PyTorch CPU port of the reference learner step on the workload's FULL batch (never a smaller one):
+    per-step wall times of `steps` steps after `warmup` untimed ones, plus the loss-only part (mask epilogue +
+    compute_loss + autograd through it, net outputs given) timed the same way."""
+    from oracle.torch_learner import CpuLearner, loss_from_raw
+    torch.set_num_threads(threads)
     args = train_args(w)
     lrn = CpuLearner(make_net(w), args, lr=3e-8 * w['B'] * w['T'])
-    B = w['B']
-    probe = make_batch(w, 1000, B=min(B, 64))
-    t0 = time.perf_counter()
-    lrn.step(probe)
-    lrn.step(probe)
-    t_probe = (time.perf_counter() - t0) / 2 * (B / probe['action'].shape[0])    # estimated full-batch step
-    if t_probe * (steps + warmup) > budget_s:
-        Bs = max(16, int(B * budget_s / (t_probe * (steps + warmup))))
-        Bs = 1 << (Bs.bit_length() - 1)
-    else:
-        Bs = B
-    batches = [make_batch(w, 2000 + i, B=Bs) for i in range(4)]
+    batches = [make_batch(w, 2000 + i) for i in range(4)]
     for i in range(warmup):
         lrn.step(batches[i % 4])
-    t0 = time.perf_counter()
+    times = []
     for i in range(steps):
+        t0 = time.perf_counter()
         lrn.step(batches[i % 4])
-    dt = time.perf_counter() - t0
-    return {'value': Bs * w['T'] * steps / dt, 'ms_per_step': dt / steps * 1e3, 'B_sample': Bs,
-            'cores': torch.get_num_threads(), 'steps': steps}
+        times.append(time.perf_counter() - t0)
+    out = {'ms_mean': 1e3 * sum(times) / len(times), 'ms_min': 1e3 * min(times), 'ms_median': 1e3 * statistics.median(times),
+           'value': w['B'] * w['T'] * len(times) / sum(times), 'cores': torch.get_num_threads(), 'steps': steps, 'warmup': warmup,
+           'total_s': sum(times)}
+    if loss_only_too:
+        from handyrl_b200.synthetic import synthetic_outputs
+        b = batches[0]
+        has_ret = w['net'] == 'geister'
+        lt = []
+        for i in range(warmup + steps):
+            raw = {k: v.requires_grad_(True) for k, v in synthetic_outputs(b, has_return=has_ret, seed=i).items()}
+            t0 = time.perf_counter()
+            losses, _ = loss_from_raw(raw, b, args)
+            losses['total'].backward()
+            if i >= warmup:
+                lt.append(time.perf_counter() - t0)
+        out['loss_only'] = {'ms_min': 1e3 * min(lt), 'ms_median': 1e3 * statistics.median(lt), 'ms_mean': 1e3 * sum(lt) / len(lt)}
+    return out
+
+
+def cpu_baseline_block(w, r, kind_note=''):
+    return {'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port',
+            'sample': '%d timed steps (after %d warm-ups) of the FULL B=%d x T=%d batch, eager-PyTorch CPU port of the reference '
+                      'step (oracle/torch_learner.py)%s' % (r['steps'], r['warmup'], w['B'], w['T'], kind_note),
+            'ms_per_step': {'min': r['ms_min'], 'median': r['ms_median'], 'mean': r['ms_mean']},
+            'loss_only_ms': r.get('loss_only'), 'host_cores': os.cpu_count()}
 
 
 def reference_arm(opt, w):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return      # the host has one set of cores: rank 0 alone measures it
-    if w['net'] == 'geister':
-        print(json.dumps({'impl': 'reference', 'unavailable': 'the CPU port (oracle/torch_learner.py) covers feed-forward nets only'}), flush=True)
-        return
-    # torchrun exports OMP_NUM_THREADS=1; the baseline gets the host's physical cores regardless (capped at 64)
-    r = run_cpu_port(w, opt.steps, opt.warmup, budget_s=150.0, threads=max(1, min(64, (os.cpu_count() or 2) // 2)))
-    sample = '%d steps of a B=%d x T=%d batch (workload B=%d)' % (opt.steps, r['B_sample'], w['T'], w['B'])
+    steps, warmup = max(1, opt.steps), max(3, opt.warmup)
+    # a probe step decides only whether the run fits the time box; the batch is never shrunk
+    probe = run_cpu_port(w, 1, 1, CPU_THREADS, loss_only_too=False)
+    est = probe['ms_mean'] * 1e-3 * (steps + warmup) * 1.3
+    if est > opt.cpu_budget_s:
+        fit = int(opt.cpu_budget_s / (probe['ms_mean'] * 1e-3 * 1.3)) - warmup
+        if fit < 3:
+            print(json.dumps({'impl': 'reference', 'unavailable': 'one CPU step of %s takes %.1f s: %d+%d steps do not fit %d s'
+                              % (opt.workload, probe['ms_mean'] * 1e-3, steps, warmup, opt.cpu_budget_s)}), flush=True)
+            return
+        steps = fit
+    r = run_cpu_port(w, steps, warmup, CPU_THREADS)
     line = {
         'impl': 'reference', 'metric': 'learner_samples_per_sec', 'value': r['value'], 'unit': 'samples/s',
-        'n_gpus': opt.gpus, 'steps': opt.steps, 'warmup': opt.warmup, 'ms_per_step': r['ms_per_step'],
+        'n_gpus': opt.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': r['ms_mean'],
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-        'config': {'workload': w['desc'], 'global_batch': r['B_sample'], 'seq_len': w['T'], 'parallelism': 'cpu'},
-        'cpu_baseline': {'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port', 'sample': sample},
+        'config': {'workload': w['desc'], 'global_batch': w['B'], 'seq_len': w['T'], 'parallelism': 'cpu', 'threads': r['cores']},
+        'cpu_baseline': cpu_baseline_block(w, r),
         'e2e': {'value': r['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -241,21 +291,115 @@ def time_loss_alone(B, T, P, A, turn_based, observation, args, device, reps):
     return {'ms': e0.elapsed_time(e1) / (rounds * n), 'bytes': per_set, 'sets': n}
 
 
+def time_gather_alone(w, device, reps=20):
+    """The replay gather/pad kernel (K2) alone: episodes of the workload's shape resident in the device ring, B windows per
+    launch into distinct output batches that together exceed L2.  Algorithmic bytes = batch bytes written + stored rows read
+    (batch bytes x live fraction)."""
+    import numpy as np
+    from handyrl_b200.batch import FlatEpisode
+    from handyrl_b200.replay import DeviceReplay
+    g = np.random.default_rng(0)
+    B, T, P, A = w['B'], w['T'], w['P'], w['A']
+    args = train_args(w)
+    obs_elems = int(np.prod(w['obs_shape']))
+    steps = 3 * T
+    n_eps = max(8, min(64, int(1.5e9 / (steps * P * (obs_elems + A) * 4))))
+    rp = DeviceReplay(capacity_steps=n_eps * steps + 1, max_episodes=n_eps + 1, device=device)
+    fes = []
+    for _ in range(n_eps):
+        fe = FlatEpisode()
+        fe.steps, fe.players = steps, list(range(P))
+        fe.obs = (g.random((steps, P) + tuple(w['obs_shape'])) < 0.3).astype(np.float32)
+        fe.prob = g.random((steps, P), dtype=np.float32)
+        fe.action = g.integers(0, A, (steps, P)).astype(np.int32)
+        fe.amask = np.where(g.random((steps, P, A)) < 0.7, 0, 1e32).astype(np.float32)
+        fe.value = g.random((steps, P, 1), dtype=np.float32)
+        fe.reward = np.zeros((steps, P), np.float32)
+        fe.ret = np.zeros((steps, P), np.float32)
+        fe.flags = np.full((steps, P), 3, np.uint8)
+        fe.turn = (np.arange(steps) % P).astype(np.int32)
+        fe.outcome = np.zeros(P, np.float32)
+        fes.append(fe)
+    rp.add_flat_many(fes)
+    probe = rp.empty_batch(B, args)
+    batch_bytes = sum(t.numel() * t.element_size() for t in probe.values())
+    n_out = max(2, min(16, int(2 * L2_BYTES / batch_bytes) + 1))
+    outs = [probe] + [rp.empty_batch(B, args) for _ in range(n_out - 1)]
+    wins = [rp.sample_windows(B, args, g) for _ in range(n_out)]
+    wdev = [torch.from_numpy(x.view(np.uint8).reshape(B, -1)).to(device) for x in wins]
+    live = float(np.mean([(x['end'] - x['start']).sum() / (B * T) for x in wins]))
+    for wd, out in zip(wdev, outs):
+        rp.gather(wd, args, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for wd, out in zip(wdev, outs):
+            rp.gather(wd, args, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (reps * n_out)
+    return {'ms': ms, 'bytes': batch_bytes * (1 + live), 'batch_bytes': batch_bytes, 'live': live, 'outputs': n_out}
+
+
+def trainer_leg(w, steps, warm_steps=100):
+    """samples/s through the drop-in Trainer: episodes (reference wire format) -> feeder thread decode + upload -> window
+    sampling -> gather/pad kernel -> learner step, with epoch hand-offs (update()) going on, over >= `steps` steps."""
+    from handyrl_b200.train import Trainer
+    from handyrl_b200.synthetic import tictactoe_episodes
+    args = dict(train_args(w), minimum_episodes=2000, maximum_episodes=20000, gpu_replay=True, num_gpus=1, forward_steps=w['T'])
+    tr = Trainer(args, make_net(w))
+    tr.episodes.extend(tictactoe_episodes(4000, seed=7))
+    stop = threading.Event()
+
+    def learner_side():          # what Learner.feed_episodes / Learner.update do while the trainer runs
+        fresh = tictactoe_episodes(2000, seed=8)
+        i = 0
+        while not stop.is_set():
+            tr.episodes.extend(fresh[i % 2000:i % 2000 + 20])
+            i += 20
+            while len(tr.episodes) > args['maximum_episodes']:
+                tr.episodes.popleft()
+            time.sleep(0.01)
+
+    th = threading.Thread(target=tr.run, daemon=True)
+    th.start()
+    tr.update()                                    # first epoch: builds + captures the step
+    feeder = threading.Thread(target=learner_side, daemon=True)
+    feeder.start()
+    while tr.steps < warm_steps:
+        time.sleep(0.001)
+    tr.stepper.stream.synchronize()
+    s0, t0 = tr.steps, time.perf_counter()
+    handoffs = 0
+    while tr.steps - s0 < steps:
+        time.sleep(0.05)
+        if handoffs < 3 and tr.steps - s0 > (handoffs + 1) * steps // 4:
+            tr.update()                            # an epoch hand-off in the middle of the timed region
+            handoffs += 1
+    tr.stepper.stream.synchronize()
+    dt, n = time.perf_counter() - t0, tr.steps - s0
+    stop.set()
+    feeder.join(timeout=5)
+    fed = tr.gpu_batcher.fed
+    tr.stop()
+    th.join(timeout=20)
+    return {'value': w['B'] * w['T'] * n / dt, 'unit': 'samples/s', 'ms_per_step': 1e3 * dt / n, 'steps': n, 'epoch_handoffs': handoffs,
+            'episodes_uploaded': fed, 'timing': 'host wall clock around the steps, stream synchronised on both sides',
+            'path': 'Trainer.run: EpisodeDeque -> GpuBatcher (feeder thread, vectorised window sampling, hrl_gather_pad) -> LearnerStep'}
+
+
 def b200_arm(opt, w):
     import torch.distributed as dist
-    from handyrl_b200 import ops
+    from handyrl_b200 import multigpu, ops
     from handyrl_b200.synthetic import bytes_per_cell
     from handyrl_b200.train import LearnerStep, PackedBatch
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
+    rank, world, local = multigpu.init_from_env('nccl')
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
-    pg = None
-    if world > 1:
-        dist.init_process_group('nccl', device_id=device)
-        pg = dist.group.WORLD
+    pinned_cpus = multigpu.pin_to_gpu_numa(local) if world > 1 else None
+    pg = dist.group.WORLD if world > 1 else None
 
     args = train_args(w)
     B, T, P, A = w['B'], w['T'], w['P'], w['A']
@@ -287,24 +431,29 @@ def b200_arm(opt, w):
             e0.record()
         for i in range(n_steps):
             fn(n_warm + i)
+        t_launched = time.perf_counter() - t0
         with torch.cuda.stream(stepper.stream):
             e1.record()
         barrier()
         wall = time.perf_counter() - t0
-        ms = e0.elapsed_time(e1)
+        mine = e0.elapsed_time(e1)
+        ms, per_rank = mine, None
         if world > 1:
-            t = torch.tensor([ms], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms, wall
+            t = torch.tensor([mine, wall * 1e3, t_launched * 1e3], device=device)
+            allt = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            ms = max(float(x[0]) for x in allt)
+            per_rank = [{'device_ms': float(x[0]), 'wall_ms': float(x[1]), 'host_launch_ms': float(x[2])} for x in allt]
+        return ms, wall, per_rank
 
+    warm = max(3, opt.warmup)
     # ---- value: inputs resident in HBM
     with ClockSampler(physical_device_index(local)) as clocks:
-        ms, wall = timed(lambda i: stepper.step_resident(dev_ring[i % R]), max(3, opt.warmup), opt.steps)
+        ms, wall, per_rank_value = timed(lambda i: stepper.step_resident(dev_ring[i % R]), warm, opt.steps)
     kernel_ms, n_k = stepper.loss_kernel_ms()
     value = B * T * world * opt.steps / (ms * 1e-3)
 
-    # ---- e2e: host batches, H2D inside, loss read back every step (lagged by one step)
+    # ---- e2e: host batches, H2D inside (copy stream, one step ahead), loss read back every step (lagged by one step)
     pending = []
 
     def e2e_step(i):
@@ -313,30 +462,44 @@ def b200_arm(opt, w):
         if len(pending) > 1:
             pending.pop(0)()
 
-    ms_e2e, wall_e2e = timed(e2e_step, max(3, opt.warmup), opt.steps)
+    ms_e2e, wall_e2e, per_rank_e2e = timed(e2e_step, warm, opt.steps)
     last = pending.pop()()
     stepper.loss_kernel_ms()
     e2e_value = B * T * world * opt.steps / (ms_e2e * 1e-3)
 
+    # ---- every rank must hold the same weights (identical clip + Adam on the all-reduced bucket)
+    ranks_identical = None
+    if world > 1:
+        if stepper.peer is not None:
+            stepper.peer.check()
+        flat = stepper.state.flat_param
+        digest = torch.stack([flat.double().sum(), (flat.double() * torch.arange(flat.numel(), device=device, dtype=torch.float64)).sum()])
+        alld = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(alld, digest)
+        ranks_identical = all(torch.equal(d, alld[0]) for d in alld)
+        assert ranks_identical, 'ranks hold different weights after %d steps: %s' % (stepper.steps, [d.tolist() for d in alld])
+
     # ---- the loss kernel alone on cold inputs (distinct input sets larger than L2), at the bench shape and at the
-    #      wide-row shape of configs[4]'s per-GPU shard (where an HBM roofline is physically meaningful)
-    alone, wide = None, None
-    if rank == 0:
+    #      wide-row shape of configs[4]'s per-GPU shard (where an HBM roofline is physically meaningful); K2 alone
+    alone, wide, k2 = None, None, None
+    if rank == 0 and not opt.quick:
         alone = time_loss_alone(B, T, P, A, w['turn_based'], w['observation'], args, device, reps=200)
         if not opt.no_wide:
             ww = WORKLOADS['cfg5shard']
             wide = time_loss_alone(ww['B'], ww['T'], ww['P'], ww['A'], ww['turn_based'], ww['observation'], train_args(ww),
                                    device, reps=40)
+            k2 = {'cfg5shard': time_gather_alone(ww, device, reps=5)}
+            if w['obs_shape'] is not None and opt.workload != 'cfg5shard':
+                k2[opt.workload] = time_gather_alone(w, device, reps=20)
 
+    launches_per_step = stepper.launches_per_step
     if rank != 0:
         shutdown(stepper, world)
         return
 
-    from handyrl_b200 import fastnet
-    n_fused_bn = sum(isinstance(m, fastnet.BoardBatchNorm2d) for m in stepper.model.modules()) if w['net'] == 'tictactoe' else 0
     peak, peak_src = measured_peak()
     Pa = example['action_mask'].shape[2]
-    alg_bytes = bytes_per_cell(P, Pa, A, T, 1 if w['net'] == 'geister' else 0) * B * T
+    alg_bytes = bytes_per_cell(P, Pa, A, T, 1 if w['net'] == 'geister' else 0) * B * (T - w.get('burn_in', 0))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     traffic, traffic_all = None, None
     try:
@@ -347,29 +510,34 @@ def b200_arm(opt, w):
         pass
     line = {
         'metric': 'learner_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': opt.steps,
-        'warmup': max(3, opt.warmup), 'ms_per_step': ms / opt.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': warm, 'ms_per_step': ms / opt.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
         'config': {'workload': w['desc'], 'global_batch': B * world, 'seq_len': T, 'parallelism': 'dp%d' % world,
-                   'tf32': False, 'cuda_graph': True,
+                   'tf32': 'single-pass TF32 disabled; the small-board dense layers run 3xTF32 (hi/lo split, fp32 accumulate) on tcgen05',
+                   'cuda_graph': True,
                    'l2': 'inputs rotate over a ring of %d distinct resident batches (%.0f MB > 126 MB L2)' % (R, R * nbytes / 1e6),
                    'batchnorm': 'per-shard statistics (as the reference DataParallel)'},
         'clocks': clocks.summary(),
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e / opt.steps,
                 'h2d_bytes_per_step': nbytes * world, 'd2h_bytes_per_step': 24 * world,
                 'wall_s': wall_e2e, 'last_losses': last},
-        # our kernels per step: loss fwd+bwd, [peer all-reduce+]grad sum-of-squares, clip+Adam, step counter,
-        # and 3 forward + 3 backward launches per fused BatchNorm layer of the (rewritten) net
-        'gpu_launches': (4 + 6 * n_fused_bn) * opt.steps,
+        # this library's kernels per step, counted by the Python wrappers while the step was captured (ops.LAUNCHES)
+        'gpu_launches': launches_per_step * opt.steps,
+        'gpu_launches_per_step': launches_per_step,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'kernel': loss_kernel_name(A) + ' (hrl_loss_fwd_bwd)', 'kernel_us': kernel_ms * 1e3,
                      'launches_timed': n_k, 'algorithmic_bytes': alg_bytes, 'peak_source': peak_src,
                      'alone_cold_us': None if alone is None else alone['ms'] * 1e3,
                      'alone_cold_gbs': None if alone is None else alg_bytes / (alone['ms'] * 1e-3) / 1e9,
-                     'note': 'event-bracketed single launch inside the step; %.2f MB per launch = %.2f us at peak%s, see '
-                             'DESIGN.md section 4' % (alg_bytes / 1e6, alg_bytes / peak / 1e3,
-                                                      ' (latency-bound: below one DRAM round trip + launch)' if alg_bytes < 2e7 else '')},
+                     'note': 'event-bracketed single launch inside the step (events + the graph boundary around it add ~10 us to a '
+                             'launch of this size, see DESIGN.md section 4); %.2f MB per launch = %.2f us at peak%s'
+                             % (alg_bytes / 1e6, alg_bytes / peak / 1e3,
+                                ' (latency-bound: below one DRAM round trip + launch)' if alg_bytes < 2e7 else '')},
         'wall_s': wall,
     }
+    if world > 1:
+        line['ranks_identical'] = ranks_identical
+        line['per_rank'] = {'value': per_rank_value, 'e2e': per_rank_e2e, 'numa_pinned_cpus': None if pinned_cpus is None else len(pinned_cpus)}
     if wide is not None:
         gbs = wide['bytes'] / (wide['ms'] * 1e-3) / 1e9
         line['roofline_wide_rows'] = {
@@ -377,14 +545,29 @@ def b200_arm(opt, w):
             'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
             'kernel': loss_kernel_name(WORKLOADS['cfg5shard']['A']) + ' (hrl_loss_fwd_bwd)', 'kernel_us': wide['ms'] * 1e3,
             'algorithmic_bytes': wide['bytes'], 'traffic': None if traffic_all is None else traffic_all.get('cfg5shard')}
-    if world == 1 and not opt.no_cpu and w['net'] != 'geister':     # the CPU port is feed-forward only
-        r = run_cpu_port(w, steps=8, warmup=1, budget_s=25.0, threads=max(1, min(64, (os.cpu_count() or 2) // 2)))
-        r1 = run_cpu_port(w, steps=4, warmup=1, budget_s=12.0, threads=1)
-        line['cpu_baseline'] = {
-            'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port',
-            'sample': '%d steps of B=%d x T=%d (eager PyTorch CPU port of the reference step, oracle/torch_learner.py)'
-                      % (r['steps'], r['B_sample'], T),
-            'as_shipped_1_thread': r1['value'], 'host_cores': os.cpu_count()}
+    if k2:
+        line['roofline_k2'] = {
+            name: {'bound': 'hbm', 'kernel': 'hrl::gather_pad_kernel (hrl_gather_pad)', 'achieved': r['bytes'] / (r['ms'] * 1e-3) / 1e9,
+                   'peak': peak, 'unit': 'GB/s', 'frac': r['bytes'] / (r['ms'] * 1e-3) / 1e9 / peak, 'kernel_us': r['ms'] * 1e3,
+                   'algorithmic_bytes': r['bytes'], 'batch_bytes': r['batch_bytes'], 'live_fraction': r['live'],
+                   'traffic': None if traffic_all is None else traffic_all.get('k2_' + name),
+                   'note': 'alone, back to back into %d output batches (> L2); algorithmic = batch bytes written + live rows read' % r['outputs']}
+            for name, r in k2.items()}
+    if world == 1 and not opt.no_trainer and not opt.quick and w['net'] == 'tictactoe':
+        try:
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):        # the Trainer prints the reference's progress lines
+                line['e2e_trainer'] = trainer_leg(w, steps=max(200, min(opt.steps, 2000)))
+        except Exception as e:  # noqa: BLE001
+            line['e2e_trainer'] = {'error': '%s: %s' % (type(e).__name__, e)}
+    if world == 1 and not opt.no_cpu and not opt.quick:
+        probe = run_cpu_port(w, 1, 1, CPU_THREADS, loss_only_too=False)
+        n = max(3, min(20, int(25.0 / (probe['ms_mean'] * 1e-3)) - 3))
+        r = run_cpu_port(w, steps=n, warmup=3, threads=CPU_THREADS)
+        line['cpu_baseline'] = cpu_baseline_block(w, r)
+        if probe['ms_mean'] < 4000:
+            r1 = run_cpu_port(w, steps=3, warmup=1, threads=1, loss_only_too=False)
+            line['cpu_baseline']['as_shipped_1_thread'] = {'value': r1['value'], 'ms_median': r1['ms_median']}
     print(json.dumps(line), flush=True)
     shutdown(stepper, world)
 
@@ -413,7 +596,10 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--no-wide', action='store_true', help='skip the wide-row loss-kernel measurement')
+    ap.add_argument('--no-wide', action='store_true', help='skip the wide-row loss-kernel and gather-kernel measurements')
+    ap.add_argument('--no-trainer', action='store_true', help='skip the Trainer (e2e_trainer) leg')
+    ap.add_argument('--quick', action='store_true', help='value and e2e only')
+    ap.add_argument('--cpu-budget-s', type=int, default=240, help='time box of --impl reference (steps are dropped, never the batch)')
     opt = ap.parse_args()
     w = WORKLOADS[opt.workload]
     if opt.impl == 'reference':

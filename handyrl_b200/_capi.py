@@ -91,7 +91,8 @@ SYMBOLS = {
     'hrl_gemm_tf32x3': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     'hrl_board_expand': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
-    'hrl_board_fold': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
+    'hrl_board_fold': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
+    'hrl_gemm_effective_splits': (C.c_int32, [C.c_int64, C.c_int32]),
     'hrl_lstm_gates_fwd': (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     'hrl_lstm_gates_bwd': (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     'hrl_hidden_visible_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

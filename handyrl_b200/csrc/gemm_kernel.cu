@@ -13,10 +13,11 @@
 // at tensor-core speed.
 //
 // Structure (one CTA = one 128-row tile of C x up to 288 columns x one slice of K):
-//   * all 8 warps are producers: global fp32 -> registers -> (hi, lo) split -> shared memory in the UMMA canonical
-//     K-major no-swizzle layout [k/4][row][4 floats] (core matrix = 8 rows x 16 bytes, SBO = 128 B, LBO = rows*16 B);
-//     either operand may be stored with its reduction dimension contiguous ("k-major") or strided (transposed on the
-//     fly: the weight-gradient product reduces over samples);
+//   * all 16 warps are producers: global fp32 -> registers -> (hi, lo) split -> shared memory in the UMMA canonical
+//     K-major SWIZZLE_128B layout (one 128-byte row per operand row and chunk, 16-byte slots XOR-swizzled by the row:
+//     conflict-free 16-byte stores both for row-contiguous and for transposing loads); either operand may be stored
+//     with its reduction dimension contiguous ("k-major") or strided (transposed on the fly: the weight-gradient
+//     product reduces over samples);
 //   * two shared-memory stages of 32 reduction elements; one elected thread issues 3 x 4 (x 2 column halves when
 //     N > 256) tcgen05.mma per stage and commits them to the stage's mbarrier, which the producers wait on before
 //     refilling the stage (TMA is not used: the operands need the hi/lo split on their way in);
@@ -64,11 +65,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 
-// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
-// version 1 <<46 | layout_type 0 <<61)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-           (1ull << 46);
+// shared-memory matrix descriptor, K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 <<16 |
+// SBO>>4 <<32 | version 1 <<46 | layout_type SWIZZLE_128B = 2 <<61).  A row of the tile is the 128 bytes (32 reduction
+// elements) of one chunk; 8-row groups are 1024 bytes apart (SBO); inside a group the 16-byte slot j of row r sits at
+// slot j ^ (r & 7) (Swizzle<3,4,3>).  LBO is not used by swizzled K-major layouts (set to 1).  The k-step inside the
+// chunk is selected by advancing the start address by 32 bytes.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
 // instruction descriptor of tcgen05.mma kind::tf32 (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major
@@ -105,26 +108,25 @@ __device__ __forceinline__ void split_tf32(const float4 v, float4 &hi, float4 &l
 // shared-memory slot per split half); their coordinates are computed once, each chunk only advances the pointers.
 struct Item {
     const float *ptr;      // first of the 4 elements in chunk 0 (valid rows only)
-    uint32_t slot;         // byte offset of the 16-byte slot inside an operand half: j * LBO + row * 16
+    uint32_t slot;         // byte offset of the 16-byte slot inside an operand half: row * 128 + ((j ^ (row & 7)) << 4)
     int k;                 // 4 * j: offset of the quad inside a chunk
     bool live;             // the row exists
 };
 
 template <bool KMAJOR>
-__device__ __forceinline__ Item make_item(int i, int n_items, const float *base, long long ld, int rows_pad, int rows, uint32_t lbo) {
+__device__ __forceinline__ Item make_item(int i, int n_items, const float *base, long long ld, int rows_pad, int rows) {
     Item it;
     int row, j;
-    if (KMAJOR) {           // a warp covers 8 rows x 4 slots: 64 contiguous bytes per row in global memory and a
-        const int blk = i >> 5, l = i & 31;      // conflict-free 128-byte run per slot column in shared memory
-        row = (blk >> 1) * 8 + (l & 7);
-        j = (blk & 1) * 4 + (l >> 3);
-    } else {                // consecutive lanes = consecutive rows (coalesced along the contiguous dimension)
-        j = i / rows_pad;
+    if (KMAJOR) {           // 8 consecutive lanes = the 128 contiguous bytes of one row's chunk: one cache line per quarter
+        row = i >> 3;       // warp in global memory, and (swizzle) 8 distinct 16-byte slots in shared memory
+        j = i & 7;
+    } else {                // consecutive lanes = consecutive rows: coalesced along the contiguous dimension, and the swizzle
+        j = i / rows_pad;   // spreads 8 consecutive rows of one slot column over 8 distinct slots
         row = i - j * rows_pad;
     }
     it.live = i < n_items && row < rows;
     it.k = 4 * j;
-    it.slot = (uint32_t)j * lbo + (uint32_t)row * 16u;
+    it.slot = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
     it.ptr = base + (KMAJOR ? (long long)row * ld + 4 * j : (long long)(4 * j) * ld + row);
     if (i >= n_items) it.slot = 0xFFFFFFFFu;
     return it;
@@ -155,7 +157,8 @@ __device__ __forceinline__ float4 load_item(const Item &it, long long ld, bool v
 
 template <bool A_K, bool B_K, int ITEMS_A, int ITEMS_B>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const GemmParams p, const int n_pad) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // swizzle atoms need 1024-byte alignment
     __shared__ __align__(8) uint64_t bars[kStages + 1];
     __shared__ uint32_t tmem_base_slot;
 
@@ -169,11 +172,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
     const int c_begin = split * p.chunks_per_split;
     const int c_end = min(total_chunks, c_begin + p.chunks_per_split);
 
-    // stage layout: [A_hi | A_lo | B_hi | B_lo], each [8 slots of 16 B][rows][16 B]
+    // stage layout: [A_hi | A_lo | B_hi | B_lo], each [rows][128 B] with the 16-byte slots of a row swizzled
     const uint32_t a_bytes = kTileM * kChunkK * 4, b_bytes = (uint32_t)n_pad * kChunkK * 4;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t lbo_a = kTileM * 16, lbo_b = (uint32_t)n_pad * 16;
 
     if (tid == 0) {
         for (int s = 0; s <= kStages; s++) mbar_init(smem_u32(&bars[s]), 1);
@@ -199,9 +201,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
 
     Item ia[ITEMS_A], ib[ITEMS_B];
 #pragma unroll
-    for (int u = 0; u < ITEMS_A; u++) ia[u] = make_item<A_K>(tid + u * kGemmThreads, kTileM * 8, Ag, p.lda, kTileM, rows_a, lbo_a);
+    for (int u = 0; u < ITEMS_A; u++) ia[u] = make_item<A_K>(tid + u * kGemmThreads, kTileM * 8, Ag, p.lda, kTileM, rows_a);
 #pragma unroll
-    for (int u = 0; u < ITEMS_B; u++) ib[u] = make_item<B_K>(tid + u * kGemmThreads, n_pad * 8, Bg, p.ldb, n_pad, n_here, lbo_b);
+    for (int u = 0; u < ITEMS_B; u++) ib[u] = make_item<B_K>(tid + u * kGemmThreads, n_pad * 8, Bg, p.ldb, n_pad, n_here);
 
     for (int c = c_begin; c < c_end; c++) {
         const int it = c - c_begin, s = it & 1;
@@ -250,14 +252,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
 #pragma unroll
             for (int ks = 0; ks < kChunkK / 8; ks++) {
                 for (int h = 0; h < halves; h++) {
-                    const uint32_t boff = 2 * ks * lbo_b + h * n_mma * 16;
-                    const uint32_t aoff = 2 * ks * lbo_a;
+                    const uint32_t boff = 32 * ks + h * n_mma * 128;      // n_mma % 8 == 0: whole swizzle atoms
+                    const uint32_t aoff = 32 * ks;
                     const uint32_t d = tmem_base + h * n_mma;
                     const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
                     // small terms first: a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
-                    umma_tf32(d, umma_desc(a_lo + aoff, lbo_a, 128), umma_desc(b_hi + boff, lbo_b, 128), idesc, first);
-                    umma_tf32(d, umma_desc(a_hi + aoff, lbo_a, 128), umma_desc(b_lo + boff, lbo_b, 128), idesc, 1u);
-                    umma_tf32(d, umma_desc(a_hi + aoff, lbo_a, 128), umma_desc(b_hi + boff, lbo_b, 128), idesc, 1u);
+                    umma_tf32(d, umma_desc(a_lo + aoff), umma_desc(b_hi + boff), idesc, first);
+                    umma_tf32(d, umma_desc(a_hi + aoff), umma_desc(b_lo + boff), idesc, 1u);
+                    umma_tf32(d, umma_desc(a_hi + aoff), umma_desc(b_hi + boff), idesc, 1u);
                 }
             }
             umma_commit(smem_u32(&bars[s]));
@@ -341,12 +343,21 @@ extern "C" size_t hrl_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int
     return splits > 1 ? (size_t)splits * (size_t)M * (size_t)N : 0;
 }
 
+// how many K slices a request for `splits` really produces (whole 32-element chunks per slice, no empty slice)
+extern "C" int32_t hrl_gemm_effective_splits(int64_t K, int32_t splits) {
+    const int total_chunks = (int)((K + hrl::kChunkK - 1) / hrl::kChunkK);
+    if (splits < 1) splits = 1;
+    if (splits > total_chunks) splits = total_chunks;
+    const int per = (total_chunks + splits - 1) / splits;
+    return (total_chunks + per - 1) / per;
+}
+
 extern "C" int hrl_gemm_tf32x3(const float *A, int64_t lda, int32_t a_kmajor, const float *B, int64_t ldb, int32_t b_kmajor,
                                const float *bias, float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t splits,
                                float *workspace, void *stream_) {
     using namespace hrl;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    HRL_REQUIRE(A && B && C, HRL_ERR_BAD_ARG, "hrl_gemm_tf32x3: NULL pointer");
+    HRL_REQUIRE(A && B && (C || (splits > 1 && workspace)), HRL_ERR_BAD_ARG, "hrl_gemm_tf32x3: NULL pointer");
     HRL_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), HRL_ERR_BAD_ARG,
                 "hrl_gemm_tf32x3: bad dimensions (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
     HRL_REQUIRE(lda >= (a_kmajor ? K : M) && ldb >= (b_kmajor ? K : N) && ldc >= N, HRL_ERR_BAD_ARG,
@@ -374,7 +385,7 @@ extern "C" int hrl_gemm_tf32x3(const float *A, int64_t lda, int32_t a_kmajor, co
     } else {
         p.C = C; p.ldc = ldc; p.c_split_stride = 0;
     }
-    const size_t smem_bytes = (size_t)kStages * (2 * (size_t)kTileM * kChunkK * 4 + 2 * (size_t)n_pad * kChunkK * 4);
+    const size_t smem_bytes = 1024 + (size_t)kStages * (2 * (size_t)kTileM * kChunkK * 4 + 2 * (size_t)n_pad * kChunkK * 4);
     const dim3 grid((unsigned)((M + kTileM - 1) / kTileM), (unsigned)n_tiles, (unsigned)splits);
     const int items_b = (n_pad * 8 + kGemmThreads - 1) / kGemmThreads;
     constexpr int IA = kTileM * 8 / kGemmThreads;
@@ -397,7 +408,7 @@ extern "C" int hrl_gemm_tf32x3(const float *A, int64_t lda, int32_t a_kmajor, co
 #undef HRL_GEMM_LAUNCH
 #undef HRL_GEMM_LAUNCH2
     HRL_CUDA_CHECK(cudaGetLastError());
-    if (splits > 1) {
+    if (splits > 1 && C != nullptr) {       // C == NULL: the caller consumes the slice partials itself (hrl_board_fold)
         const long long n = (long long)M * N;
         HRL_REQUIRE(ldc == N, HRL_ERR_UNSUPPORTED, "hrl_gemm_tf32x3: split-K output must be dense (ldc == N)");
         int blocks = (int)((n + 255) / 256);

@@ -29,23 +29,29 @@ __global__ void board_expand_kernel(const float *__restrict__ w, float *__restri
     }
 }
 
-__global__ void board_fold_kernel(const float *__restrict__ ddense, float *__restrict__ dw, int Cout, int Cin, int kh, int kw, int H,
-                                  int W) {
+// one warp per weight element: lanes stride over the K-slice partials of the dense gradient (fixed order -> deterministic)
+__global__ void board_fold_kernel(const float *__restrict__ ddense, int splits, long long split_stride, float *__restrict__ dw, int Cout,
+                                  int Cin, int kh, int kw, int H, int W) {
     const int HW = H * W;
     const int n = Cout * Cin * kh * kw;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < n; idx += (gridDim.x * blockDim.x) >> 5) {
         const int b = idx % kw, a = (idx / kw) % kh, i = (idx / (kw * kh)) % Cin, o = idx / (kw * kh * Cin);
         float s = 0.f;
-        for (int qy = 0; qy < H; qy++) {
-            const int py = qy + a - kh / 2;
-            if (py < 0 || py >= H) continue;
-            for (int qx = 0; qx < W; qx++) {
-                const int px = qx + b - kw / 2;
-                if (px < 0 || px >= W) continue;
-                s += __ldg(ddense + (long long)(o * HW + qy * W + qx) * (Cin * HW) + i * HW + py * W + px);
+        for (int sp = lane; sp < splits; sp += 32) {
+            const float *d = ddense + (long long)sp * split_stride;
+            for (int qy = 0; qy < H; qy++) {
+                const int py = qy + a - kh / 2;
+                if (py < 0 || py >= H) continue;
+                for (int qx = 0; qx < W; qx++) {
+                    const int px = qx + b - kw / 2;
+                    if (px < 0 || px >= W) continue;
+                    s += __ldg(d + (long long)(o * HW + qy * W + qx) * (Cin * HW) + i * HW + py * W + px);
+                }
             }
         }
-        dw[idx] = s;
+        s = warp_sum(s);
+        if (lane == 0) dw[idx] = s;
     }
 }
 
@@ -182,12 +188,12 @@ extern "C" int hrl_board_expand(const float *w, float *dense, int32_t Cout, int3
     return HRL_OK;
 }
 
-extern "C" int hrl_board_fold(const float *ddense, float *dw, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W,
-                              void *stream) {
-    HRL_REQUIRE(ddense && dw && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && H > 0 && W > 0 && (kh & 1) && (kw & 1), HRL_ERR_BAD_ARG,
-                "hrl_board_fold: NULL pointer or bad shape (odd kernels only)");
-    board_fold_kernel<<<grid_for((long long)Cout * Cin * kh * kw), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ddense, dw, Cout, Cin,
-                                                                                                                     kh, kw, H, W);
+extern "C" int hrl_board_fold(const float *ddense, int32_t splits, int64_t split_stride, float *dw, int32_t Cout, int32_t Cin, int32_t kh,
+                              int32_t kw, int32_t H, int32_t W, void *stream) {
+    HRL_REQUIRE(ddense && dw && splits >= 1 && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && H > 0 && W > 0 && (kh & 1) && (kw & 1),
+                HRL_ERR_BAD_ARG, "hrl_board_fold: NULL pointer or bad shape (odd kernels only)");
+    board_fold_kernel<<<grid_for((long long)Cout * Cin * kh * kw * 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        ddense, splits, split_stride, dw, Cout, Cin, kh, kw, H, W);
     HRL_CUDA_CHECK(cudaGetLastError());
     return HRL_OK;
 }

@@ -11,6 +11,15 @@ import torch
 from . import _capi
 from ._capi import ALGO_ID, LOSS_KEYS, NUM_LOSS, HrlLossArgs, check, lib
 
+# kernels of THIS library launched through the wrappers below (bench.py reports them as `gpu_launches`; a CUDA graph
+# replays the launches counted while it was captured)
+LAUNCHES = {'n': 0}
+
+
+def _count(n=1):
+    LAUNCHES['n'] += n
+
+
 _BATCH_KEYS = ('action_mask', 'action', 'selected_prob', 'reward', 'return', 'turn_mask', 'observation_mask',
                'episode_mask', 'progress', 'outcome')
 
@@ -92,6 +101,7 @@ def loss_fwd_bwd(outputs, batch, args, buffers=None, taps=False, tuning=None):
     cached = getattr(buffers, '_cached', None)
     if cached is not None and cached[0] == key:
         check(lib().hrl_loss_fwd_bwd(C.byref(cached[1]), _stream_ptr()))
+        _count()
         return buffers
 
     a = HrlLossArgs()
@@ -137,6 +147,7 @@ def loss_fwd_bwd(outputs, batch, args, buffers=None, taps=False, tuning=None):
         if t:
             raise ValueError('unknown loss tuning keys: %s' % sorted(t))
     check(lib().hrl_loss_fwd_bwd(C.byref(a), _stream_ptr()))
+    _count()
     buffers._keep = keep  # the launch is asynchronous: keep temporaries alive
     if all(k is None or k is o for k, o in zip(keep[3:], (batch['action_mask'], batch['action'], batch['selected_prob'],
                                                           batch['reward'], batch['return'], batch['turn_mask'],
@@ -166,6 +177,7 @@ def compute_target(algorithm, values, returns, rewards, lmb, gamma, rhos, cs, ma
     check(lib().hrl_compute_target(aid, B, T, P, Tr, Pr, _ptr(values), _ptr(returns), _ptr(rewards), float(lmb),
                                    float(gamma), _ptr(rhos), _ptr(cs), _ptr(masks), _ptr(targets), _ptr(advantages),
                                    _stream_ptr()))
+    _count()
     return targets, advantages
 
 
@@ -233,6 +245,7 @@ class FlatAdam:
                                        self.n_pad, _ptr(self.partials), _ptr(self.lr), _ptr(self.step_count), self.max_norm,
                                        self.betas[0], self.betas[1], self.eps, self.weight_decay, _ptr(self.grad_norm),
                                        _stream_ptr()))
+        _count(2)
 
     def step(self):
         s = _stream_ptr()
@@ -241,6 +254,7 @@ class FlatAdam:
                                        _ptr(self.exp_avg_sq), self.n_pad, _ptr(self.partials), _ptr(self.lr),
                                        _ptr(self.step_count), self.max_norm, self.betas[0], self.betas[1], self.eps,
                                        self.weight_decay, _ptr(self.grad_norm), s))
+        _count(3)
 
 
 def gemm_tf32x3(a, b, bias=None, a_kmajor=True, b_kmajor=True, splits=1, out=None):
@@ -260,6 +274,7 @@ def gemm_tf32x3(a, b, bias=None, a_kmajor=True, b_kmajor=True, splits=1, out=Non
         ws = torch.empty(lib().hrl_gemm_workspace_floats(M, N, K, splits), dtype=torch.float32, device=a.device)
     check(lib().hrl_gemm_tf32x3(_ptr(a), a.stride(0), int(a_kmajor), _ptr(b), b.stride(0), int(b_kmajor), _ptr(bias), _ptr(out),
                                 out.stride(0), M, N, K, splits, _ptr(ws), _stream_ptr()))
+    _count(2 if splits > 1 else 1)
     return out
 
 
@@ -303,6 +318,7 @@ class _BoardDense(torch.autograd.Function):
         ctx.dims = (Cout, Cin, kh, kw, H, W)
         dense = torch.empty((Cout * H * W, Cin * H * W), dtype=torch.float32, device=weight.device)
         check(lib().hrl_board_expand(_ptr(weight), _ptr(dense), Cout, Cin, kh, kw, H, W, _stream_ptr()))
+        _count()
         return dense
 
     @staticmethod
@@ -310,12 +326,64 @@ class _BoardDense(torch.autograd.Function):
         Cout, Cin, kh, kw, H, W = ctx.dims
         ddense = ddense.contiguous()
         dw = torch.empty((Cout, Cin, kh, kw), dtype=torch.float32, device=ddense.device)
-        check(lib().hrl_board_fold(_ptr(ddense), _ptr(dw), Cout, Cin, kh, kw, H, W, _stream_ptr()))
+        check(lib().hrl_board_fold(_ptr(ddense), 1, 0, _ptr(dw), Cout, Cin, kh, kw, H, W, _stream_ptr()))
+        _count()
         return dw, None, None
 
 
 def board_dense(weight, H, W):
     return _BoardDense.apply(weight, H, W)
+
+
+class _BoardConv(torch.autograd.Function):
+    """A stride-1 "same" convolution over a tiny board, NCHW in and out, as dense products on the tensor cores:
+    forward   y = x2d @ dense(w)^T            (hrl_board_expand + hrl_gemm_tf32x3)
+    backward  dx = dy2d @ dense(w)            (hrl_gemm_tf32x3, the dense matrix read as stored)
+              dw = fold(sum_s dy2d_s^T x2d_s) (split-K hrl_gemm_tf32x3 leaving its slice partials, folded AND summed by
+                                               one hrl_board_fold launch: no dense gradient is ever materialised)"""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        x = x.contiguous()
+        weight = weight.contiguous()
+        N, Cin, H, W = x.shape
+        Cout, _, kh, kw = weight.shape
+        dense = torch.empty((Cout * H * W, Cin * H * W), dtype=torch.float32, device=x.device)
+        check(lib().hrl_board_expand(_ptr(weight), _ptr(dense), Cout, Cin, kh, kw, H, W, _stream_ptr()))
+        _count()
+        y = gemm_tf32x3(x.view(N, Cin * H * W), dense)
+        ctx.save_for_backward(x, dense)
+        ctx.dims = (N, Cin, H, W, Cout, kh, kw)
+        return y.view(N, Cout, H, W)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, dense = ctx.saved_tensors
+        N, Cin, H, W, Cout, kh, kw = ctx.dims
+        dy2 = dy.contiguous().view(N, Cout * H * W)
+        x2 = x.view(N, Cin * H * W)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_tf32x3(dy2, dense, b_kmajor=False).view(N, Cin, H, W)
+        if ctx.needs_input_grad[1]:
+            rows, cols = Cout * H * W, Cin * H * W
+            tiles = ((rows + 127) // 128) * ((cols + 287) // 288)
+            splits = lib().hrl_gemm_effective_splits(N, max(1, min(N // 64, 148 // tiles)))
+            dw = torch.empty((Cout, Cin, kh, kw), dtype=torch.float32, device=dy.device)
+            if splits > 1:
+                ws = torch.empty(splits * rows * cols, dtype=torch.float32, device=dy.device)
+                check(lib().hrl_gemm_tf32x3(_ptr(dy2), dy2.stride(0), 0, _ptr(x2), x2.stride(0), 0, None, None, cols, rows, cols, N,
+                                            splits, _ptr(ws), _stream_ptr()))
+            else:
+                ws = gemm_tf32x3(dy2, x2, a_kmajor=False, b_kmajor=False).view(-1)
+                _count(-1)
+            check(lib().hrl_board_fold(_ptr(ws), splits, rows * cols, _ptr(dw), Cout, Cin, kh, kw, H, W, _stream_ptr()))
+            _count(2)
+        return dx, dw
+
+
+def board_conv(x, weight):
+    return _BoardConv.apply(x, weight)
 
 
 class _LstmGates(torch.autograd.Function):
@@ -326,6 +394,7 @@ class _LstmGates(torch.autograd.Function):
         S = gates[0, 0].numel()
         h, c = torch.empty_like(c_prev), torch.empty_like(c_prev)
         check(lib().hrl_lstm_gates_fwd(_ptr(gates), _ptr(c_prev), _ptr(h), _ptr(c), N, C4 // 4, S, _stream_ptr()))
+        _count()
         ctx.save_for_backward(gates, c_prev)
         return h, c
 
@@ -338,6 +407,7 @@ class _LstmGates(torch.autograd.Function):
         check(lib().hrl_lstm_gates_bwd(_ptr(gates), _ptr(c_prev), _ptr(None if dh is None else dh.contiguous()),
                                        _ptr(None if dc is None else dc.contiguous()), _ptr(dgates), _ptr(dc_prev), N, C4 // 4, S,
                                        _stream_ptr()))
+        _count()
         return dgates, dc_prev
 
 
@@ -361,6 +431,7 @@ class _HiddenVisible(torch.autograd.Function):
         om, stride = _mask_view(om)
         out = torch.empty((B,) + tuple(h.shape[2:]) if sum_players else h.shape, dtype=torch.float32, device=h.device)
         check(lib().hrl_hidden_visible_fwd(_ptr(h), _ptr(om), stride, _ptr(out), B, P, R, int(sum_players), _stream_ptr()))
+        _count()
         ctx.save_for_backward(om)
         ctx.meta = (B, P, R, stride, bool(sum_players), tuple(h.shape))
         return out
@@ -371,6 +442,7 @@ class _HiddenVisible(torch.autograd.Function):
         B, P, R, stride, sum_players, shape = ctx.meta
         dh = torch.empty(shape, dtype=torch.float32, device=dout.device)
         check(lib().hrl_hidden_visible_bwd(_ptr(dout.contiguous()), _ptr(om), stride, _ptr(dh), B, P, R, int(sum_players), _stream_ptr()))
+        _count()
         return dh, None, None
 
 
@@ -384,6 +456,7 @@ class _HiddenBlend(torch.autograd.Function):
         om, stride = _mask_view(om)
         out = torch.empty_like(h)
         check(lib().hrl_hidden_blend_fwd(_ptr(h), _ptr(nh), _ptr(om), stride, _ptr(out), B, P, Pn, R, _stream_ptr()))
+        _count()
         ctx.save_for_backward(om)
         ctx.meta = (B, P, Pn, R, stride, tuple(h.shape), tuple(nh.shape))
         return out
@@ -395,6 +468,7 @@ class _HiddenBlend(torch.autograd.Function):
         dh = torch.empty(hshape, dtype=torch.float32, device=dout.device) if ctx.needs_input_grad[0] else None
         dnh = torch.empty(nshape, dtype=torch.float32, device=dout.device)
         check(lib().hrl_hidden_blend_bwd(_ptr(dout.contiguous()), _ptr(om), stride, _ptr(dh), _ptr(dnh), B, P, Pn, R, _stream_ptr()))
+        _count()
         return dh, dnh, None
 
 
@@ -422,6 +496,7 @@ class _BatchNormTrain(torch.autograd.Function):
         ws = torch.empty(lib().hrl_bn_workspace_floats(N, Cn, H * W), dtype=torch.float32, device=x.device)
         check(lib().hrl_bn_train_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(running_mean),
                                      _ptr(running_var), N, Cn, H * W, float(eps), float(momentum), _ptr(ws), _stream_ptr()))
+        _count(3)
         ctx.save_for_backward(x, weight, mean, rstd)
         return y
 
@@ -436,6 +511,7 @@ class _BatchNormTrain(torch.autograd.Function):
         ws = torch.empty(lib().hrl_bn_workspace_floats(N, Cn, H * W), dtype=torch.float32, device=x.device)
         check(lib().hrl_bn_train_bwd(_ptr(x), _ptr(dy), _ptr(weight), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
                                      N, Cn, H * W, _ptr(ws), _stream_ptr()))
+        _count(3)
         return dx, (dgamma if weight is not None else None), (dbeta if ctx.needs_input_grad[2] else None), None, None, None, None
 
 
@@ -491,4 +567,5 @@ class PeerAllReduce:
         check(lib().hrl_peer_allreduce_sumsq(_ptr(self.reduced), _ptr(self.peer_ptrs), self.numel, self.world, self.rank,
                                              self.numel, n_norm, _ptr(partials), _ptr(self.epoch), _ptr(self.ticket),
                                              _ptr(self.status), _stream_ptr()))
+        _count(1)
         return self.reduced

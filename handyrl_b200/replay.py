@@ -280,6 +280,8 @@ class DeviceReplay:
         g.episode_mask, g.turn_mask, g.observation_mask = ptr(out['episode_mask']), ptr(out['turn_mask']), ptr(out['observation_mask'])
         g.action_mask, g.progress = ptr(out['action_mask']), ptr(out['progress'])
         check(lib().hrl_gather_pad(C.byref(g), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        from . import ops
+        ops._count()
         out['_windows'] = wdev      # keep the descriptor buffer alive until the kernel has run
         return out
 

@@ -131,6 +131,53 @@ def synthetic_geese_batch(B, T, P, A=4, *, seed=0, board=(7, 11), planes=17):
     return batch
 
 
+def tictactoe_episodes(n, *, seed=0, compress_steps=4, gamma=0.8):
+    """n self-play games of 3x3 noughts-and-crosses between uniformly random players, in the reference's episode wire
+    format (generation.py:84-91: {'args', 'steps', 'outcome', 'moment': [bz2(pickle(list of moments))...]}, a moment
+    holding per-player observation / selected_prob / action_mask / action / value / reward / return and 'turn';
+    only the turn player acts and observes, generation.py:35-40).  Stands in for the worker processes as the episode
+    source of bench.py's trainer leg: the learner consumes these exactly as it consumes the workers' episodes."""
+    import bz2
+    import pickle
+    import random
+    import numpy as np
+    rng = random.Random(seed)
+    lines = [(0, 1, 2), (3, 4, 5), (6, 7, 8), (0, 3, 6), (1, 4, 7), (2, 5, 8), (0, 4, 8), (2, 4, 6)]
+    keys = ('observation', 'selected_prob', 'action_mask', 'action', 'value', 'reward', 'return')
+    episodes = []
+    for _ in range(n):
+        board = [0] * 9                       # +1 first player's stones, -1 second player's
+        moments, winner = [], None
+        for ply in range(9):
+            player = ply % 2
+            colour = 1 if player == 0 else -1
+            legal = [a for a in range(9) if board[a] == 0]
+            grid = np.array(board, np.float32).reshape(3, 3)
+            obs = np.stack([np.ones((3, 3), np.float32), (grid == colour).astype(np.float32), (grid == -colour).astype(np.float32)])
+            mask = np.full(9, 1e32, np.float32)
+            mask[legal] = 0
+            action = rng.choice(legal)
+            m = {k: {0: None, 1: None} for k in keys}
+            m['observation'][player] = obs
+            m['selected_prob'][player] = np.float32(1.0 / len(legal))
+            m['action_mask'][player] = mask
+            m['action'][player] = action
+            m['value'][player] = np.array([rng.uniform(-0.5, 0.5)], np.float32)
+            m['reward'] = {0: 0, 1: 0}
+            m['return'] = {0: 0.0, 1: 0.0}
+            m['turn'] = [player]
+            moments.append(m)
+            board[action] = colour
+            if any(board[a] == board[b] == board[c] == colour for a, b, c in lines):
+                winner = player
+                break
+        outcome = {0: 0, 1: 0} if winner is None else {winner: 1, 1 - winner: -1}
+        episodes.append({'args': {'role': 'g', 'player': [0, 1], 'model_id': {0: 0, 1: 0}}, 'steps': len(moments), 'outcome': outcome,
+                         'moment': [bz2.compress(pickle.dumps(moments[i:i + compress_steps]))
+                                    for i in range(0, len(moments), compress_steps)]})
+    return episodes
+
+
 def synthetic_outputs(batch, *, has_value=True, has_return=False, seed=1):
     """Raw net outputs for kernel-only tests: policy ~ N(0,1), value = tanh(N(0,1))."""
     g = torch.Generator().manual_seed(seed)

@@ -380,6 +380,9 @@ class LearnerStep:
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self._handoff_slots = None
         self._handoff_i = 0
+        self._staging = None
+        self._staging_i = 0
+        self.launches_per_step = 0
         self.ema = torch.full((1,), float(example_batch['action'].shape[0] * args.get('forward_steps', 1)) * self.world,
                               dtype=torch.float32, device=self.device)
 
@@ -465,8 +468,10 @@ class LearnerStep:
         with torch.cuda.stream(self.stream):
             self.dev_buffer.copy_(self._warm.buffer, non_blocking=True)
             state = self._snapshot()
-            for _ in range(3):
+            for i in range(3):
+                before = ops.LAUNCHES['n']
                 self._device_step()
+                self.launches_per_step = ops.LAUNCHES['n'] - before      # this library's kernels in one step
             self.stream.synchronize()
             self._restore(state)
             if self.use_graph and not self.time_loss_kernel:
@@ -526,13 +531,31 @@ class LearnerStep:
     def _enqueue(self, src_bytes, packed):
         if not getattr(self, '_captured', False):
             self._capture()
+        if packed is not None:
+            # host batch: the H2D copy runs on the copy stream into one of two staging buffers, i.e. while the previous
+            # step still computes; the step stream only waits for it and moves the bytes device-to-device (~1 us)
+            if self._staging is None:
+                self._staging = [torch.empty_like(self.dev_buffer) for _ in range(2)]
+                self._staging_free = [None, None]
+            k = self._staging_i % 2
+            self._staging_i += 1
+            with torch.cuda.stream(self.copy_stream):
+                if self._staging_free[k] is not None:
+                    self.copy_stream.wait_event(self._staging_free[k])
+                self._staging[k].copy_(src_bytes, non_blocking=True)
+                arrived = torch.cuda.Event()
+                arrived.record(self.copy_stream)
+            packed.in_flight = arrived
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(arrived)
+                self.dev_buffer.copy_(self._staging[k], non_blocking=True)
+                freed = torch.cuda.Event()
+                freed.record(self.stream)
+                self._staging_free[k] = freed
+            src_bytes = None
         with torch.cuda.stream(self.stream):
             if src_bytes is not None:
                 self.dev_buffer.copy_(src_bytes, non_blocking=True)
-            if packed is not None:
-                ev = torch.cuda.Event()
-                ev.record(self.stream)
-                packed.in_flight = ev
             if not self.use_graph:
                 self._device_step()
             elif not self.time_loss_kernel:

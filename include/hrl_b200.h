@@ -196,10 +196,12 @@ int hrl_peer_allreduce_sumsq(float *out_sum, const float *const *peer_buckets, i
  *                        0: at  k * ld + row  (the operand is stored transposed, e.g. reduce over samples)
  *   splits               K slices computed by separate CTAs into `workspace` (hrl_gemm_workspace_floats floats) and
  *                        summed in a fixed order (deterministic); 1 = no split, workspace may be NULL.  A split
- *                        product takes no bias and needs ldc == N.
+ *                        product takes no bias and needs ldc == N; with C == NULL the slice partials
+ *                        (hrl_gemm_effective_splits of them, M*N floats apart) are left in the workspace.
  * Relative error ~1e-6 of sum_k |a||b| (plain fp32 summation is ~1e-7 * sqrt(K)); NOT the 1e-3 of single-pass TF32.
  */
 size_t hrl_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int32_t splits);
+int32_t hrl_gemm_effective_splits(int64_t K, int32_t splits);   /* slices really produced (whole 32-element chunks) */
 int hrl_gemm_tf32x3(const float *A, int64_t lda, int32_t a_kmajor, const float *B, int64_t ldb, int32_t b_kmajor,
                     const float *bias, float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t splits,
                     float *workspace, void *stream);
@@ -208,12 +210,13 @@ int hrl_gemm_tf32x3(const float *A, int64_t lda, int32_t a_kmajor, const float *
  * Weight of a stride-1 "same" convolution (Cout,Cin,kh,kw; odd kernel, zero padding) <-> the dense matrix
  * (Cout*H*W, Cin*H*W) that applies it to an H x W board stored NCHW (fastnet.BoardConv2d), and the adjoint map
  * dense-gradient -> weight-gradient.  dense[(o,q),(i,p)] = w[o,i,a,b] where tap (a,b) makes output cell q read input
- * cell p, 0 if no tap does.
+ * cell p, 0 if no tap does.  hrl_board_fold sums `splits` dense gradients `split_stride` floats apart (the K-slice
+ * partials a split hrl_gemm_tf32x3 leaves in its workspace when called with C == NULL; 1 for a single matrix).
  */
 int hrl_board_expand(const float *w, float *dense, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W,
                      void *stream);
-int hrl_board_fold(const float *ddense, float *dw, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W,
-                   void *stream);
+int hrl_board_fold(const float *ddense, int32_t splits, int64_t split_stride, float *dw, int32_t Cout, int32_t Cin, int32_t kh,
+                   int32_t kw, int32_t H, int32_t W, void *stream);
 
 /*
  * Recurrent nets.  ConvLSTM gate arithmetic (reference geister.py:49-56): gates (N,4C,S) in the order
