@@ -29,29 +29,39 @@ __global__ void board_expand_kernel(const float *__restrict__ w, float *__restri
     }
 }
 
-// one warp per weight element: lanes stride over the K-slice partials of the dense gradient (fixed order -> deterministic)
+// one CTA per output channel o: its HW rows of the dense gradient (a contiguous slab of HW * Cin*HW floats per K slice) are
+// summed over the slices with coalesced reads (fixed order -> deterministic) into shared memory, then folded onto the taps
 __global__ void board_fold_kernel(const float *__restrict__ ddense, int splits, long long split_stride, float *__restrict__ dw, int Cout,
                                   int Cin, int kh, int kw, int H, int W) {
-    const int HW = H * W;
-    const int n = Cout * Cin * kh * kw;
-    const int lane = threadIdx.x & 31;
-    for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < n; idx += (gridDim.x * blockDim.x) >> 5) {
-        const int b = idx % kw, a = (idx / kw) % kh, i = (idx / (kw * kh)) % Cin, o = idx / (kw * kh * Cin);
+    extern __shared__ float slab[];                   // [HW][Cin*HW]
+    const int HW = H * W, cols = Cin * HW, n = HW * cols;
+    const int o = blockIdx.x;
+    const float *base = ddense + (long long)o * n;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int sp = 0;
+        for (; sp + 8 <= splits; sp += 8) {           // eight independent loads in flight per thread (latency-bound otherwise)
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc[u] += __ldg(base + (long long)(sp + u) * split_stride + e);
+        }
+        for (; sp < splits; sp++) acc[0] += __ldg(base + (long long)sp * split_stride + e);
+        slab[e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    }
+    __syncthreads();
+    const int taps = kh * kw;
+    for (int t = threadIdx.x; t < Cin * taps; t += blockDim.x) {
+        const int i = t / taps, a = (t % taps) / kw, b = t % kw;
         float s = 0.f;
-        for (int sp = lane; sp < splits; sp += 32) {
-            const float *d = ddense + (long long)sp * split_stride;
-            for (int qy = 0; qy < H; qy++) {
-                const int py = qy + a - kh / 2;
-                if (py < 0 || py >= H) continue;
-                for (int qx = 0; qx < W; qx++) {
-                    const int px = qx + b - kw / 2;
-                    if (px < 0 || px >= W) continue;
-                    s += __ldg(d + (long long)(o * HW + qy * W + qx) * (Cin * HW) + i * HW + py * W + px);
-                }
+        for (int qy = 0; qy < H; qy++) {
+            const int py = qy + a - kh / 2;
+            if (py < 0 || py >= H) continue;
+            for (int qx = 0; qx < W; qx++) {
+                const int px = qx + b - kw / 2;
+                if (px < 0 || px >= W) continue;
+                s += slab[(qy * W + qx) * cols + i * HW + py * W + px];
             }
         }
-        s = warp_sum(s);
-        if (lane == 0) dw[idx] = s;
+        dw[((long long)(o * Cin + i) * kh + a) * kw + b] = s;
     }
 }
 
@@ -192,8 +202,13 @@ extern "C" int hrl_board_fold(const float *ddense, int32_t splits, int64_t split
                               int32_t kw, int32_t H, int32_t W, void *stream) {
     HRL_REQUIRE(ddense && dw && splits >= 1 && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && H > 0 && W > 0 && (kh & 1) && (kw & 1),
                 HRL_ERR_BAD_ARG, "hrl_board_fold: NULL pointer or bad shape (odd kernels only)");
-    board_fold_kernel<<<grid_for((long long)Cout * Cin * kh * kw * 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        ddense, splits, split_stride, dw, Cout, Cin, kh, kw, H, W);
+    const size_t slab_bytes = (size_t)H * W * Cin * H * W * sizeof(float);
+    HRL_REQUIRE(slab_bytes <= 200 * 1024, HRL_ERR_UNSUPPORTED, "hrl_board_fold: Cin*(H*W)^2 = %zu floats exceed shared memory",
+                slab_bytes / sizeof(float));
+    if (slab_bytes > 48 * 1024)
+        HRL_CUDA_CHECK(cudaFuncSetAttribute(board_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab_bytes));
+    board_fold_kernel<<<Cout, 1024, slab_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(ddense, splits, split_stride, dw, Cout, Cin, kh, kw,
+                                                                                         H, W);
     HRL_CUDA_CHECK(cudaGetLastError());
     return HRL_OK;
 }

@@ -52,19 +52,19 @@ def test_board_conv_on_tensor_cores_matches_conv2d(board, chans):
     fast = nn.Conv2d(chans[0], chans[1], k, padding=k // 2).cuda()
     fast.load_state_dict(ref.state_dict())
     fastnet.optimize_small_boards(nn.Sequential(fast))
+    ref = ref.double()          # float64 reference (cuDNN's autotuned fp32 algorithms are themselves only ~1e-3 accurate)
     x = torch.randn(700, chans[0], *board, device='cuda')
-    xr, xf = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
-    torch.backends.cudnn.allow_tf32 = False
+    xr, xf = x.double().requires_grad_(True), x.clone().requires_grad_(True)
     before = fastnet.BoardConv2d.dense_calls
     yr, yf = ref(xr), fast(xf)
     assert fastnet.BoardConv2d.dense_calls == before + 1
-    dy = torch.randn_like(yr)
-    yr.backward(dy)
+    dy = torch.randn_like(yf)
+    yr.backward(dy.double())
     yf.backward(dy)
-    torch.testing.assert_close(yf, yr, rtol=1e-4, atol=2e-5)
-    torch.testing.assert_close(xf.grad, xr.grad, rtol=1e-4, atol=2e-5)
-    torch.testing.assert_close(fast.weight.grad, ref.weight.grad, rtol=1e-4, atol=2e-4)      # sums over 700 x cells terms
-    torch.testing.assert_close(fast.bias.grad, ref.bias.grad, rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(yf.double(), yr, rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(xf.grad.double(), xr.grad, rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(fast.weight.grad.double(), ref.weight.grad, rtol=1e-5, atol=1e-4)      # sums of 700 x cells terms
+    torch.testing.assert_close(fast.bias.grad.double(), ref.bias.grad, rtol=1e-5, atol=1e-4)
 
 
 def test_lstm_gates_kernel_matches_torch():
