@@ -134,3 +134,22 @@ def clip_adam(param, grad, m, v, lr, step, max_norm=4.0, b1=0.9, b2=0.999, eps=1
         assert x.dtype == np.float32 and x.flags.c_contiguous
     return lib().hrl_oracle_clip_adam(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.size, lr, step,
                                       max_norm, b1, b2, eps, wd)
+
+
+def board_conv(x, w, b=None):
+    """Reference of a stride-1 "same" convolution over a small board (what torch.nn.functional.conv2d computes inside the
+    user's net, reference envs/tictactoe.py:20-31): plain float64 loops over taps, NCHW.  Checker of the tensor-core dense
+    path (hrl_board_expand + hrl_gemm_tf32x3) in __graft_entry__.smoke() and the tests."""
+    x = np.asarray(x, np.float64)
+    w = np.asarray(w, np.float64)
+    N, Cin, H, W = x.shape
+    Cout, _, kh, kw = w.shape
+    xp = np.zeros((N, Cin, H + kh - 1, W + kw - 1))
+    xp[:, :, kh // 2:kh // 2 + H, kw // 2:kw // 2 + W] = x
+    y = np.zeros((N, Cout, H, W))
+    for a in range(kh):
+        for c in range(kw):
+            y += np.einsum('nihw,oi->nohw', xp[:, :, a:a + H, c:c + W], w[:, :, a, c])
+    if b is not None:
+        y += np.asarray(b, np.float64).reshape(1, Cout, 1, 1)
+    return y
