@@ -50,6 +50,22 @@ class HrlLossArgs(C.Structure):
     ]
 
 
+class HrlGemmOperand(C.Structure):
+    _fields_ = [('ptr', C.c_void_p), ('ptr2', C.c_void_p), ('p', C.c_void_p), ('q', C.c_void_p), ('r', C.c_void_p),
+                ('ld', C.c_int64), ('kmajor', C.c_int32), ('relu', C.c_int32), ('feature_is_row', C.c_int32)]
+
+
+GEMM_EPILOGUES = {'store': 0, 'relu': 1, 'stats': 2, 'mask_stats': 3}
+
+
+class HrlGemmArgs(C.Structure):
+    _fields_ = [('a', HrlGemmOperand), ('b', HrlGemmOperand), ('bias', C.c_void_p), ('C', C.c_void_p),
+                ('ldc', C.c_int64), ('M', C.c_int64), ('N', C.c_int64), ('K', C.c_int64),
+                ('splits', C.c_int32), ('epilogue', C.c_int32), ('workspace', C.c_void_p),
+                ('ep_y', C.c_void_p), ('ep_ldy', C.c_int64), ('ep_scale', C.c_void_p), ('ep_shift', C.c_void_p),
+                ('ep_mean', C.c_void_p), ('ep_rstd', C.c_void_p), ('col_partials', C.c_void_p)]
+
+
 class HrlWindow(C.Structure):
     _fields_ = [('first_step', C.c_int64), ('start', C.c_int32), ('end', C.c_int32),
                 ('train_start', C.c_int32), ('total', C.c_int32), ('outcome_row', C.c_int32),
@@ -90,6 +106,13 @@ SYMBOLS = {
     'hrl_gemm_workspace_floats': (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64, C.c_int32]),
     'hrl_gemm_tf32x3': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    'hrl_gemm_fused': (C.c_int, [C.POINTER(HrlGemmArgs), C.c_void_p]),
+    'hrl_bn_finalize_fwd': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_float] +
+                            [C.c_void_p] * 8),
+    'hrl_bn_finalize_bwd': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 9),
+    'hrl_heads_num_blocks': (C.c_int32, [C.c_int64]),
+    'hrl_heads_fwd': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_int32] * 5 + [C.c_float] + [C.c_void_p] * 7),
+    'hrl_heads_bwd': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_int32] * 5 + [C.c_float] + [C.c_void_p] * 16),
     'hrl_board_expand': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     'hrl_board_fold': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     'hrl_gemm_effective_splits': (C.c_int32, [C.c_int64, C.c_int32]),

@@ -25,6 +25,7 @@
 //     (one lane quarter per warp), adds the bias and stores.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -36,14 +37,28 @@ constexpr int kMaxN = 288;          // columns of one CTA tile (TMEM: 512 fp32 c
 constexpr int kChunkK = 32;         // reduction elements per shared-memory stage
 constexpr int kStages = 2;
 
+struct GemmOperand {
+    const float *ptr, *ptr2;        // ptr2: optional second source with the same layout (operand = x*p + y*q + r), or NULL
+    const float *p, *q, *r;         // per-feature constants of the operand transform, or NULL (plain operand)
+    long long ld;
+    int kmajor;                     // 1: element (row,k) at row*ld + k ; 0: at k*ld + row
+    int relu;                       // clamp the transformed operand at 0
+    int feature_is_row;             // constants indexed by the operand's row (else by the reduction index k)
+};
+
 struct GemmParams {
-    const float *A, *B, *bias;
+    GemmOperand a, b;
+    const float *bias;
     float *C;
-    long long lda, ldb, ldc;
+    long long ldc;
     long long c_split_stride;       // elements between the partial outputs of consecutive K slices
     int M, N, K;
-    int a_kmajor, b_kmajor;         // 1: element (r,k) at r*ld + k ; 0: at k*ld + r
     int chunks_per_split;
+    int epilogue;                   // HrlGemmEpilogue
+    const float *ep_y;              // masked epilogue: the pre-activation tile (M x N, leading dimension ep_ldy)
+    long long ep_ldy;
+    const float *ep_scale, *ep_shift, *ep_mean, *ep_rstd;     // per column, may be NULL
+    float *col_partials;            // [row tiles][2][N] column sums of the epilogues that produce statistics
     int debug;                      // profiling only: 1 = no MMAs, 2 = no loads/stores
 };
 
@@ -110,11 +125,12 @@ struct Item {
     const float *ptr;      // first of the 4 elements in chunk 0 (valid rows only)
     uint32_t slot;         // byte offset of the 16-byte slot inside an operand half: row * 128 + ((j ^ (row & 7)) << 4)
     int k;                 // 4 * j: offset of the quad inside a chunk
+    int row;               // operand row (for per-row transform constants)
     bool live;             // the row exists
 };
 
 template <bool KMAJOR>
-__device__ __forceinline__ Item make_item(int i, int n_items, const float *base, long long ld, int rows_pad, int rows) {
+__device__ __forceinline__ Item make_item(int i, int n_items, const float *base, long long ld, int rows_pad, int rows, int row0) {
     Item it;
     int row, j;
     if (KMAJOR) {           // 8 consecutive lanes = the 128 contiguous bytes of one row's chunk: one cache line per quarter
@@ -126,6 +142,7 @@ __device__ __forceinline__ Item make_item(int i, int n_items, const float *base,
     }
     it.live = i < n_items && row < rows;
     it.k = 4 * j;
+    it.row = row0 + row;
     it.slot = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
     it.ptr = base + (KMAJOR ? (long long)row * ld + 4 * j : (long long)(4 * j) * ld + row);
     if (i >= n_items) it.slot = 0xFFFFFFFFu;
@@ -152,6 +169,42 @@ __device__ __forceinline__ float4 load_item(const Item &it, long long ld, bool v
     if (it.k + 1 < k_left) v.y = __ldg(q + st);
     if (it.k + 2 < k_left) v.z = __ldg(q + 2 * st);
     if (it.k + 3 < k_left) v.w = __ldg(q + 3 * st);
+    return v;
+}
+
+// operand transform v = x*p[f] + y*q[f] + r[f] (relu optional) on the 4 elements of an item; elements outside the operand
+// (dead rows, reduction tail) stay exactly zero.  f = the operand row, or the reduction index k0 + it.k + e.
+__device__ __forceinline__ float4 transform_item(const GemmOperand &op, const Item &it, float4 x, float4 y, int k0, int k_left) {
+    if (op.p == nullptr || !it.live) return x;
+    float4 pp, qq = make_float4(0.f, 0.f, 0.f, 0.f), rr;
+    if (op.feature_is_row) {
+        const float a = __ldg(op.p + it.row), c = __ldg(op.r + it.row);
+        pp = make_float4(a, a, a, a);
+        rr = make_float4(c, c, c, c);
+        if (op.q != nullptr) { const float bq = __ldg(op.q + it.row); qq = make_float4(bq, bq, bq, bq); }
+    } else {
+        const int f = k0 + it.k;
+        if (it.k + 3 < k_left) {                   // k0 and it.k are multiples of 4: aligned vector loads of the constants
+            pp = __ldg(reinterpret_cast<const float4 *>(op.p + f));
+            rr = __ldg(reinterpret_cast<const float4 *>(op.r + f));
+            if (op.q != nullptr) qq = __ldg(reinterpret_cast<const float4 *>(op.q + f));
+        } else {
+            pp = rr = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (it.k + 0 < k_left) { pp.x = __ldg(op.p + f); rr.x = __ldg(op.r + f); if (op.q) qq.x = __ldg(op.q + f); }
+            if (it.k + 1 < k_left) { pp.y = __ldg(op.p + f + 1); rr.y = __ldg(op.r + f + 1); if (op.q) qq.y = __ldg(op.q + f + 1); }
+            if (it.k + 2 < k_left) { pp.z = __ldg(op.p + f + 2); rr.z = __ldg(op.r + f + 2); if (op.q) qq.z = __ldg(op.q + f + 2); }
+        }
+    }
+    float4 v;
+    v.x = fmaf(x.x, pp.x, fmaf(y.x, qq.x, rr.x));
+    v.y = fmaf(x.y, pp.y, fmaf(y.y, qq.y, rr.y));
+    v.z = fmaf(x.z, pp.z, fmaf(y.z, qq.z, rr.z));
+    v.w = fmaf(x.w, pp.w, fmaf(y.w, qq.w, rr.w));
+    if (op.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (it.k + 0 >= k_left) v.x = 0.f;
+    if (it.k + 1 >= k_left) v.y = 0.f;
+    if (it.k + 2 >= k_left) v.z = 0.f;
+    if (it.k + 3 >= k_left) v.w = 0.f;
     return v;
 }
 
@@ -191,33 +244,50 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
 
-    const float *Ag = p.A + (A_K ? (long long)m0 * p.lda : (long long)m0);
-    const float *Bg = p.B + (B_K ? (long long)n0 * p.ldb : (long long)n0);
-    const bool vec_a = A_K && (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
-    const bool vec_b = B_K && (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
+    const long long off_a = A_K ? (long long)m0 * p.a.ld : (long long)m0;
+    const long long off_b = B_K ? (long long)n0 * p.b.ld : (long long)n0;
+    const float *Ag = p.a.ptr + off_a;
+    const float *Bg = p.b.ptr + off_b;
+    const long long a2 = p.a.ptr2 ? (p.a.ptr2 - p.a.ptr) : 0, b2 = p.b.ptr2 ? (p.b.ptr2 - p.b.ptr) : 0;   // second sources
+    const bool vec_a = A_K && (p.a.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a.ptr) & 15) == 0) &&
+                       (!p.a.ptr2 || (reinterpret_cast<uintptr_t>(p.a.ptr2) & 15) == 0);
+    const bool vec_b = B_K && (p.b.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.b.ptr) & 15) == 0) &&
+                       (!p.b.ptr2 || (reinterpret_cast<uintptr_t>(p.b.ptr2) & 15) == 0);
     const int halves = n_pad > 256 ? 2 : 1;
     const int n_mma = n_pad / halves;
     const uint32_t idesc = umma_idesc_tf32(kTileM, n_mma);
 
     Item ia[ITEMS_A], ib[ITEMS_B];
 #pragma unroll
-    for (int u = 0; u < ITEMS_A; u++) ia[u] = make_item<A_K>(tid + u * kGemmThreads, kTileM * 8, Ag, p.lda, kTileM, rows_a);
+    for (int u = 0; u < ITEMS_A; u++) ia[u] = make_item<A_K>(tid + u * kGemmThreads, kTileM * 8, Ag, p.a.ld, kTileM, rows_a, m0);
 #pragma unroll
-    for (int u = 0; u < ITEMS_B; u++) ib[u] = make_item<B_K>(tid + u * kGemmThreads, n_pad * 8, Bg, p.ldb, n_pad, n_here);
+    for (int u = 0; u < ITEMS_B; u++) ib[u] = make_item<B_K>(tid + u * kGemmThreads, n_pad * 8, Bg, p.b.ld, n_pad, n_here, n0);
 
     for (int c = c_begin; c < c_end; c++) {
         const int it = c - c_begin, s = it & 1;
         const int k0 = c * kChunkK;
         const int k_left = p.K - k0;
-        const long long adv_a = A_K ? (long long)k0 : (long long)k0 * p.lda;
-        const long long adv_b = B_K ? (long long)k0 : (long long)k0 * p.ldb;
+        const long long adv_a = A_K ? (long long)k0 : (long long)k0 * p.a.ld;
+        const long long adv_b = B_K ? (long long)k0 : (long long)k0 * p.b.ld;
         // ---- global loads of this chunk (issued before waiting for the stage: latency overlaps the running MMAs)
         float4 va[ITEMS_A], vb[ITEMS_B];
         if (p.debug != 2) {
 #pragma unroll
-            for (int u = 0; u < ITEMS_A; u++) va[u] = load_item<A_K>(ia[u], p.lda, vec_a, adv_a, k_left);
+            for (int u = 0; u < ITEMS_A; u++) {
+                va[u] = load_item<A_K>(ia[u], p.a.ld, vec_a, adv_a, k_left);
+                if (p.a.p != nullptr) {
+                    const float4 y = p.a.ptr2 ? load_item<A_K>(ia[u], p.a.ld, vec_a, adv_a + a2, k_left) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    va[u] = transform_item(p.a, ia[u], va[u], y, k0, k_left);
+                }
+            }
 #pragma unroll
-            for (int u = 0; u < ITEMS_B; u++) vb[u] = load_item<B_K>(ib[u], p.ldb, vec_b, adv_b, k_left);
+            for (int u = 0; u < ITEMS_B; u++) {
+                vb[u] = load_item<B_K>(ib[u], p.b.ld, vec_b, adv_b, k_left);
+                if (p.b.p != nullptr) {
+                    const float4 y = p.b.ptr2 ? load_item<B_K>(ib[u], p.b.ld, vec_b, adv_b + b2, k_left) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    vb[u] = transform_item(p.b, ib[u], vb[u], y, k0, k_left);
+                }
+            }
         }
         if (it >= kStages) mbar_wait(smem_u32(&bars[s]), ((it >> 1) - 1) & 1);      // the MMAs that read this stage are done
         if (p.debug != 2) {
@@ -307,15 +377,87 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
     }
     __syncthreads();
     {
+        // copy-out: a warp owns rows warp, warp+16, ...; a lane owns the float4 column groups lane, lane+32, lane+64.
+        //   HRL_GEMM_EP_RELU        C = max(acc, 0)
+        //   HRL_GEMM_EP_STATS       C = acc, plus per-column sum and sum of squares over the tile's rows
+        //   HRL_GEMM_EP_MASK_STATS  C = acc * (z > 0) with z = y*scale+shift of the pre-activation tile y (the ReLU
+        //                           backward), plus per-column sums of C and of C * xhat, xhat = (y - mean) * rstd
+        //                           (the two batch sums the BatchNorm backward needs)
         const bool vec_c = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cg) & 15) == 0) && (n0 % 4 == 0) && (n_here % 4 == 0);
         const int lane = tid & 31;
-        for (int r = warp; r < rows_a; r += kGemmThreads / 32) {
-            const float *src = tile + r * ldt;
-            float *dst = Cg + (long long)(m0 + r) * p.ldc + n0;
-            if (vec_c) {
-                for (int c4 = lane; c4 < n_here / 4; c4 += 32) reinterpret_cast<float4 *>(dst)[c4] = reinterpret_cast<const float4 *>(src)[c4];
-            } else {
-                for (int c1 = lane; c1 < n_here; c1 += 32) dst[c1] = src[c1];
+        const int ep = p.epilogue;
+        const bool stats = (ep == HRL_GEMM_EP_STATS || ep == HRL_GEMM_EP_MASK_STATS) && p.col_partials != nullptr;
+        constexpr int kGroupsPerLane = (kMaxN / 4 + 31) / 32;      // 3
+        float s1[kGroupsPerLane][4], s2[kGroupsPerLane][4];
+#pragma unroll
+        for (int g = 0; g < kGroupsPerLane; g++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) s1[g][e] = s2[g][e] = 0.f;
+        if (vec_c && (ep == HRL_GEMM_EP_STORE || ep == HRL_GEMM_EP_RELU || ((ep == HRL_GEMM_EP_STATS || ep == HRL_GEMM_EP_MASK_STATS)))) {
+            const bool vec_y = ep == HRL_GEMM_EP_MASK_STATS && (p.ep_ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.ep_y) & 15) == 0);
+            for (int r = warp; r < rows_a; r += kGemmThreads / 32) {
+                const float *src = tile + r * ldt;
+                float *dst = Cg + (long long)(m0 + r) * p.ldc + n0;
+#pragma unroll
+                for (int g = 0; g < kGroupsPerLane; g++) {
+                    const int c4 = lane + 32 * g;
+                    if (c4 >= n_here / 4) break;
+                    float4 v = reinterpret_cast<const float4 *>(src)[c4];
+                    if (ep == HRL_GEMM_EP_RELU) {
+                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                    } else if (ep == HRL_GEMM_EP_STATS) {
+                        s1[g][0] += v.x; s1[g][1] += v.y; s1[g][2] += v.z; s1[g][3] += v.w;
+                        s2[g][0] = fmaf(v.x, v.x, s2[g][0]); s2[g][1] = fmaf(v.y, v.y, s2[g][1]);
+                        s2[g][2] = fmaf(v.z, v.z, s2[g][2]); s2[g][3] = fmaf(v.w, v.w, s2[g][3]);
+                    } else if (ep == HRL_GEMM_EP_MASK_STATS) {
+                        const int col = n0 + 4 * c4;
+                        const float *yp = p.ep_y + (long long)(m0 + r) * p.ep_ldy + col;
+                        float4 y;
+                        if (vec_y) y = __ldg(reinterpret_cast<const float4 *>(yp));
+                        else y = make_float4(__ldg(yp), __ldg(yp + 1), __ldg(yp + 2), __ldg(yp + 3));
+                        float yv[4] = {y.x, y.y, y.z, y.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float sc = p.ep_scale ? __ldg(p.ep_scale + col + e) : 1.f, sh = p.ep_shift ? __ldg(p.ep_shift + col + e) : 0.f;
+                            const float z = fmaf(yv[e], sc, sh);
+                            const float d = z > 0.f ? vv[e] : 0.f;
+                            const float xh = p.ep_mean ? (yv[e] - __ldg(p.ep_mean + col + e)) * __ldg(p.ep_rstd + col + e) : yv[e];
+                            vv[e] = d;
+                            s1[g][e] += d;
+                            s2[g][e] = fmaf(d, xh, s2[g][e]);
+                        }
+                        v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                    }
+                    reinterpret_cast<float4 *>(dst)[c4] = v;
+                }
+            }
+        } else {
+            for (int r = warp; r < rows_a; r += kGemmThreads / 32) {
+                const float *src = tile + r * ldt;
+                float *dst = Cg + (long long)(m0 + r) * p.ldc + n0;
+                for (int c1 = lane; c1 < n_here; c1 += 32) dst[c1] = (ep == HRL_GEMM_EP_RELU) ? fmaxf(src[c1], 0.f) : src[c1];
+            }
+        }
+        if (stats) {
+            // per-warp column sums -> shared memory (behind the tile) -> fixed-order sum over the 16 warps -> global partials
+            float *red = tile + kTileM * ldt;                 // [16 warps][2][n_pad]
+#pragma unroll
+            for (int g = 0; g < kGroupsPerLane; g++) {
+                const int c4 = lane + 32 * g;
+                if (c4 < n_pad / 4) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        red[(warp * 2 + 0) * n_pad + 4 * c4 + e] = s1[g][e];
+                        red[(warp * 2 + 1) * n_pad + 4 * c4 + e] = s2[g][e];
+                    }
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < 2 * n_here; i += kGemmThreads) {
+                const int which = i / n_here, col = i - which * n_here;
+                float acc = 0.f;
+                for (int w = 0; w < kGemmThreads / 32; w++) acc += red[(w * 2 + which) * n_pad + col];
+                p.col_partials[((long long)blockIdx.x * 2 + which) * p.N + n0 + col] = acc;
             }
         }
     }
@@ -352,38 +494,58 @@ extern "C" int32_t hrl_gemm_effective_splits(int64_t K, int32_t splits) {
     return (total_chunks + per - 1) / per;
 }
 
-extern "C" int hrl_gemm_tf32x3(const float *A, int64_t lda, int32_t a_kmajor, const float *B, int64_t ldb, int32_t b_kmajor,
-                               const float *bias, float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t splits,
-                               float *workspace, void *stream_) {
+extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
     using namespace hrl;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    HRL_REQUIRE(A && B && (C || (splits > 1 && workspace)), HRL_ERR_BAD_ARG, "hrl_gemm_tf32x3: NULL pointer");
+    HRL_REQUIRE(args != nullptr, HRL_ERR_BAD_ARG, "hrl_gemm_fused: args is NULL");
+    const HrlGemmArgs &g = *args;
+    const int64_t M = g.M, N = g.N, K = g.K;
+    int splits = g.splits;
+    HRL_REQUIRE(g.a.ptr && g.b.ptr && (g.C || (splits > 1 && g.workspace)), HRL_ERR_BAD_ARG, "hrl_gemm_fused: NULL pointer");
     HRL_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), HRL_ERR_BAD_ARG,
-                "hrl_gemm_tf32x3: bad dimensions (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
-    HRL_REQUIRE(lda >= (a_kmajor ? K : M) && ldb >= (b_kmajor ? K : N) && ldc >= N, HRL_ERR_BAD_ARG,
-                "hrl_gemm_tf32x3: leading dimension smaller than the row length");
+                "hrl_gemm_fused: bad dimensions (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
+    HRL_REQUIRE(g.a.ld >= (g.a.kmajor ? K : M) && g.b.ld >= (g.b.kmajor ? K : N) && (g.C == nullptr || g.ldc >= N), HRL_ERR_BAD_ARG,
+                "hrl_gemm_fused: leading dimension smaller than the row length");
+    HRL_REQUIRE((g.a.p == nullptr) == (g.a.r == nullptr) && (g.b.p == nullptr) == (g.b.r == nullptr) &&
+                    (g.a.ptr2 == nullptr || (g.a.p && g.a.q)) && (g.b.ptr2 == nullptr || (g.b.p && g.b.q)),
+                HRL_ERR_BAD_ARG, "hrl_gemm_fused: an operand transform needs p and r (and q with a second source)");
+    HRL_REQUIRE(g.epilogue >= HRL_GEMM_EP_STORE && g.epilogue <= HRL_GEMM_EP_MASK_STATS, HRL_ERR_BAD_ARG, "hrl_gemm_fused: unknown epilogue");
+    HRL_REQUIRE(g.epilogue != HRL_GEMM_EP_MASK_STATS || (g.ep_y != nullptr && g.ep_ldy >= N && (g.ep_mean == nullptr) == (g.ep_rstd == nullptr)),
+                HRL_ERR_BAD_ARG, "hrl_gemm_fused: the masked epilogue needs the pre-activation tile");
+    HRL_REQUIRE(g.epilogue < HRL_GEMM_EP_STATS || (N % 4 == 0 && g.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && g.col_partials),
+                HRL_ERR_UNSUPPORTED, "hrl_gemm_fused: the statistics epilogues need N and ldc multiples of 4, a 16-byte aligned C and col_partials");
     const int total_chunks = (int)((K + kChunkK - 1) / kChunkK);
     if (splits < 1) splits = 1;
     if (splits > total_chunks) splits = total_chunks;
-    HRL_REQUIRE(splits == 1 || (workspace != nullptr && bias == nullptr), HRL_ERR_WORKSPACE,
-                "hrl_gemm_tf32x3: a split-K product needs a workspace of hrl_gemm_workspace_floats() floats and no bias");
+    HRL_REQUIRE(splits == 1 || (g.workspace != nullptr && g.bias == nullptr && g.epilogue == HRL_GEMM_EP_STORE), HRL_ERR_WORKSPACE,
+                "hrl_gemm_fused: a split-K product needs a workspace of hrl_gemm_workspace_floats() floats, no bias and the plain epilogue");
     const int n_tiles = (int)((N + kMaxN - 1) / kMaxN);
     const int n_widest = (int)(N < kMaxN ? N : kMaxN);
     int n_pad = (n_widest + 15) / 16 * 16;
     if (n_pad > 256) n_pad = (n_pad + 31) / 32 * 32;
 
     GemmParams p;
-    p.A = A; p.B = B; p.bias = bias;
-    p.lda = lda; p.ldb = ldb;
+    auto operand = [](const HrlGemmOperand &o) {
+        GemmOperand r;
+        r.ptr = o.ptr; r.ptr2 = o.ptr2; r.p = o.p; r.q = o.q; r.r = o.r; r.ld = o.ld;
+        r.kmajor = o.kmajor ? 1 : 0; r.relu = o.relu ? 1 : 0; r.feature_is_row = o.feature_is_row ? 1 : 0;
+        return r;
+    };
+    p.a = operand(g.a);
+    p.b = operand(g.b);
+    p.bias = g.bias;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
-    p.a_kmajor = a_kmajor ? 1 : 0; p.b_kmajor = b_kmajor ? 1 : 0;
     p.chunks_per_split = (total_chunks + splits - 1) / splits;
+    p.epilogue = g.epilogue;
+    p.ep_y = g.ep_y; p.ep_ldy = g.ep_ldy;
+    p.ep_scale = g.ep_scale; p.ep_shift = g.ep_shift; p.ep_mean = g.ep_mean; p.ep_rstd = g.ep_rstd;
+    p.col_partials = g.col_partials;
     p.debug = g_gemm_debug;
     splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;      // no empty slices
     if (splits > 1) {
-        p.C = workspace; p.ldc = N; p.c_split_stride = M * N;
+        p.C = g.workspace; p.ldc = N; p.c_split_stride = M * N;
     } else {
-        p.C = C; p.ldc = ldc; p.c_split_stride = 0;
+        p.C = g.C; p.ldc = g.ldc; p.c_split_stride = 0;
     }
     const size_t smem_bytes = 1024 + (size_t)kStages * (2 * (size_t)kTileM * kChunkK * 4 + 2 * (size_t)n_pad * kChunkK * 4);
     const dim3 grid((unsigned)((M + kTileM - 1) / kTileM), (unsigned)n_tiles, (unsigned)splits);
@@ -397,9 +559,9 @@ extern "C" int hrl_gemm_tf32x3(const float *A, int64_t lda, int32_t a_kmajor, co
     }
 #define HRL_GEMM_LAUNCH(IB)                                                                    \
     {                                                                                         \
-        if (p.a_kmajor && p.b_kmajor) HRL_GEMM_LAUNCH2(true, true, IB)                        \
-        else if (p.a_kmajor) HRL_GEMM_LAUNCH2(true, false, IB)                                \
-        else if (p.b_kmajor) HRL_GEMM_LAUNCH2(false, true, IB)                                \
+        if (p.a.kmajor && p.b.kmajor) HRL_GEMM_LAUNCH2(true, true, IB)                        \
+        else if (p.a.kmajor) HRL_GEMM_LAUNCH2(true, false, IB)                                \
+        else if (p.b.kmajor) HRL_GEMM_LAUNCH2(false, true, IB)                                \
         else HRL_GEMM_LAUNCH2(false, false, IB)                                               \
     }
     if (items_b <= 1) HRL_GEMM_LAUNCH(1)
@@ -408,13 +570,25 @@ extern "C" int hrl_gemm_tf32x3(const float *A, int64_t lda, int32_t a_kmajor, co
 #undef HRL_GEMM_LAUNCH
 #undef HRL_GEMM_LAUNCH2
     HRL_CUDA_CHECK(cudaGetLastError());
-    if (splits > 1 && C != nullptr) {       // C == NULL: the caller consumes the slice partials itself (hrl_board_fold)
+    if (splits > 1 && g.C != nullptr) {       // C == NULL: the caller consumes the slice partials itself (hrl_board_fold)
         const long long n = (long long)M * N;
-        HRL_REQUIRE(ldc == N, HRL_ERR_UNSUPPORTED, "hrl_gemm_tf32x3: split-K output must be dense (ldc == N)");
+        HRL_REQUIRE(g.ldc == N, HRL_ERR_UNSUPPORTED, "hrl_gemm_fused: split-K output must be dense (ldc == N)");
         int blocks = (int)((n + 255) / 256);
         if (blocks > 1184) blocks = 1184;
-        sum_partials_kernel<<<blocks, 256, 0, stream>>>(workspace, splits, n, n, C);
+        sum_partials_kernel<<<blocks, 256, 0, stream>>>(g.workspace, splits, n, n, g.C);
         HRL_CUDA_CHECK(cudaGetLastError());
     }
     return HRL_OK;
+}
+
+extern "C" int hrl_gemm_tf32x3(const float *A, int64_t lda, int32_t a_kmajor, const float *B, int64_t ldb, int32_t b_kmajor,
+                               const float *bias, float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t splits,
+                               float *workspace, void *stream) {
+    HrlGemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.a.ptr = A; g.a.ld = lda; g.a.kmajor = a_kmajor;
+    g.b.ptr = B; g.b.ld = ldb; g.b.kmajor = b_kmajor;
+    g.bias = bias; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.splits = splits; g.workspace = workspace;
+    g.epilogue = HRL_GEMM_EP_STORE;
+    return hrl_gemm_fused(&g, stream);
 }

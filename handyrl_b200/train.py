@@ -338,7 +338,7 @@ class LearnerStep:
 
     def __init__(self, model, args, example_batch, lr, device=None, process_group=None, use_graph=True,
                  max_norm=4.0, weight_decay=1e-5, time_loss_kernel=False, channels_last=True, cudnn_benchmark=True,
-                 small_boards=True, peer_allreduce=None, allow_tf32=None):
+                 small_boards=True, peer_allreduce=None, allow_tf32=None, fused_tower=True):
         self.device = torch.device(device if device is not None else 'cuda')
         self.args = args
         # the learner owns its precision contract (1e-5 of the reference's fp32 arithmetic): PyTorch's default lets
@@ -352,6 +352,7 @@ class LearnerStep:
         # cuDNN's default heuristics pick FFT / NCHW-spatial kernels that are 5x slower than its NHWC
         # implicit-GEMM kernels on the tiny boards of these games; NHWC + autotune is a pure layout choice
         # tiny boards: convolutions as one SGEMM, BatchNorm as fused reductions (fastnet.py); NCHW stays as is
+        self.engine = None          # hand-scheduled fused forward/backward for recognised architectures (tower.py)
         self.rewritten = fastnet.optimize_small_boards(self.model) if small_boards else 0
         if self.rewritten and channels_last:
             channels_last = not self._uses_dense_convs(example_batch)       # dense products want NCHW-flat activations
@@ -396,6 +397,10 @@ class LearnerStep:
         self.hidden0 = None
         if hasattr(self.model, 'init_hidden'):
             self.hidden0 = tree_map(lambda h: h.to(self.device), self.model.init_hidden([B, P]))
+        from . import tower
+        if fused_tower and small_boards and self.hidden0 is None and tower.supports(self.model) and \
+                torch.is_tensor(example_batch['observation']) and example_batch['observation'].shape[-2] * example_batch['observation'].shape[-1] <= 16:
+            self.engine = tower.FusedBoardNet(self.model, B * T * Pa, self.device)
         self.loss_buf = None
         self.last_losses = torch.zeros(NUM_LOSS, device=self.device)
         self.loss_accum = torch.zeros(NUM_LOSS, dtype=torch.float64, device=self.device)
@@ -425,7 +430,12 @@ class LearnerStep:
     # -- the device work of one step, on the current stream (inputs already in self.dev)
     def _part_forward(self):
         self.opt.zero_grad()
-        self._outs = forward_raw(self.model, self.hidden0, self.dev, self.args, self.memory_format)
+        if self.engine is not None:
+            B, T, P, Pa, A = self.dims
+            flat = self.engine.forward(self.dev['observation'].flatten(0, 2))
+            self._outs = {k: v.unflatten(0, (B, T, Pa)) for k, v in flat.items()}
+        else:
+            self._outs = forward_raw(self.model, self.hidden0, self.dev, self.args, self.memory_format)
         if self.loss_buf is None:
             B, T, P, Pa, A = self.dims
             self.loss_buf = ops.LossBuffers(B, T, P, Pa, A, 'value' in self._outs, 'return' in self._outs, self.device)
@@ -437,14 +447,18 @@ class LearnerStep:
 
     def _part_backward(self):
         outs, buf = self._outs, self.loss_buf
-        heads, grads = [outs['policy']], [buf.dpolicy]
-        if 'value' in outs:
-            heads.append(outs['value'])
-            grads.append(buf.dvalue)
-        if 'return' in outs:
-            heads.append(outs['return'])
-            grads.append(buf.dreturn)
-        torch.autograd.backward(heads, grads)
+        if self.engine is not None:
+            self.engine.backward(buf.dpolicy.flatten(0, 2), buf.dvalue.flatten(0, 2),
+                                 buf.dreturn.flatten(0, 2) if buf.dreturn is not None else None)
+        else:
+            heads, grads = [outs['policy']], [buf.dpolicy]
+            if 'value' in outs:
+                heads.append(outs['value'])
+                grads.append(buf.dvalue)
+            if 'return' in outs:
+                heads.append(outs['return'])
+                grads.append(buf.dreturn)
+            torch.autograd.backward(heads, grads)
         self.opt.extra_slots[:NUM_LOSS].copy_(buf.losses)     # the loss sums ride the gradient bucket
         if self.peer is not None:
             reduced = self.peer(self.opt.n_pad, self.opt.partials)      # all-reduce + norm partials, one kernel

@@ -207,6 +207,77 @@ int hrl_gemm_tf32x3(const float *A, int64_t lda, int32_t a_kmajor, const float *
                     float *workspace, void *stream);
 
 /*
+ * The same product with the elementwise neighbours of a conv -> BatchNorm -> ReLU tower fused into it, so that a layer of
+ * the user's net is ONE launch per direction (forward / input gradient / weight gradient) instead of a product plus
+ * separate normalisation, activation and reduction passes over the (samples x features) activations:
+ *   operand transform   v = x * p[f] + y * q[f] + r[f], optionally clamped at 0, applied while the operand is staged:
+ *                       BatchNorm-apply + ReLU of the previous layer (x = its raw output, p = gamma*rstd, r = beta - mean*p),
+ *                       or the BatchNorm backward dY = dZ*p + Y*q + r (x = dZ, y = Y).  f = the reduction index, or the
+ *                       operand row when feature_is_row (transposed operands of the weight-gradient product).
+ *   epilogues           RELU: C = max(acc + bias, 0).  STATS: C = acc and per-column sum / sum of squares of the tile
+ *                       (BatchNorm batch statistics of this layer's output).  MASK_STATS: C = acc * (z > 0) with
+ *                       z = y*scale + shift of the pre-activation y (ReLU backward) and per-column sums of C and
+ *                       C * (y - mean) * rstd (the two batch sums of the BatchNorm backward).
+ * Column sums land in col_partials[row_tile][2][N] (row_tile = ceil(M/128) tiles, summed by hrl_bn_finalize_*).
+ */
+typedef struct HrlGemmOperand {
+    const float *ptr;            /* the operand as it lies in memory                                   */
+    const float *ptr2;           /* optional second source with the same layout (y above), or NULL     */
+    const float *p, *q, *r;      /* per-feature constants, NULL = plain operand (q only with ptr2)     */
+    int64_t ld;
+    int32_t kmajor;              /* 1: element (row,k) at row*ld + k; 0: at k*ld + row                 */
+    int32_t relu;
+    int32_t feature_is_row;
+} HrlGemmOperand;
+
+typedef enum { HRL_GEMM_EP_STORE = 0, HRL_GEMM_EP_RELU = 1, HRL_GEMM_EP_STATS = 2, HRL_GEMM_EP_MASK_STATS = 3 } HrlGemmEpilogue;
+
+typedef struct HrlGemmArgs {
+    HrlGemmOperand a, b;         /* C[M x N] = A_op[M x K] * B_op[N x K]^T                            */
+    const float *bias;           /* per column, or NULL                                                */
+    float *C;
+    int64_t ldc, M, N, K;
+    int32_t splits;              /* as hrl_gemm_tf32x3 (plain epilogue only)                           */
+    int32_t epilogue;            /* HrlGemmEpilogue                                                    */
+    float *workspace;
+    const float *ep_y;           /* MASK_STATS: pre-activation tile (M x N)                            */
+    int64_t ep_ldy;
+    const float *ep_scale, *ep_shift;   /* per column; NULL = 1 / 0                                    */
+    const float *ep_mean, *ep_rstd;     /* per column; NULL = second sum is sum(C * y)                 */
+    float *col_partials;         /* [ceil(M/128)][2][N] floats, or NULL                                */
+} HrlGemmArgs;
+
+int hrl_gemm_fused(const HrlGemmArgs *args, void *stream);
+
+/*
+ * Glue of a fused conv -> BatchNorm -> ReLU tower over a tiny board (handyrl_b200/tower.py: the architecture of the
+ * reference's SimpleConv2dModel, envs/tictactoe.py:52-69, with every layer ONE hrl_gemm_fused launch per direction).
+ *   hrl_bn_finalize_fwd   col_partials [tiles][2][C*HW] (column sum / sum of squares from the STATS epilogue) -> batch
+ *                         statistics of nn.BatchNorm2d in training mode (running stats with `momentum`, unbiased running
+ *                         variance, num_batches_tracked += 1) and per-COLUMN mean / rstd / scale = gamma*rstd /
+ *                         shift = beta - mean*scale (each C*HW floats) for the next product's operand transform
+ *   hrl_bn_finalize_bwd   col_partials (column sums of dZ and dZ*xhat from the MASK_STATS epilogue) -> dgamma, dbeta and
+ *                         the per-column constants of dY = dZ*p + Y*q + r.  gamma == NULL: only dbeta (a plain bias).
+ *   hrl_heads_fwd / _bwd  squeeze outputs pre (M, ld), columns [pmaps*cells | vmaps*cells | rmaps*cells] -> LeakyReLU(slope)
+ *                         -> policy = . Wp^T (A x pmaps*cells), value = tanh(. Wv^T), return = . Wr^T; the backward
+ *                         writes dpre and the gradients of Wp / Wv / Wr and of the squeeze biases (fixed-order sums;
+ *                         workspace: hrl_heads_num_blocks(M) * (A*pin + vin + rin + maps) floats).
+ */
+int hrl_bn_finalize_fwd(const float *col_partials, int32_t tiles, int32_t C, int32_t HW, int64_t rows, const float *gamma,
+                        const float *beta, float eps, float momentum, float *running_mean, float *running_var,
+                        int64_t *batches_tracked, float *mean_col, float *rstd_col, float *scale_col, float *shift_col, void *stream);
+int hrl_bn_finalize_bwd(const float *col_partials, int32_t tiles, int32_t C, int32_t HW, int64_t rows, const float *gamma,
+                        const float *mean_col, const float *rstd_col, float *dgamma, float *dbeta, float *p_col, float *q_col,
+                        float *r_col, void *stream);
+int32_t hrl_heads_num_blocks(int64_t M);
+int hrl_heads_fwd(const float *pre, int64_t ld, int64_t M, int32_t cells, int32_t pmaps, int32_t vmaps, int32_t rmaps, int32_t A,
+                  float slope, const float *Wp, const float *Wv, const float *Wr, float *policy, float *value, float *ret, void *stream);
+int hrl_heads_bwd(const float *pre, int64_t ld, int64_t M, int32_t cells, int32_t pmaps, int32_t vmaps, int32_t rmaps, int32_t A,
+                  float slope, const float *Wp, const float *Wv, const float *Wr, const float *value, const float *dpolicy,
+                  const float *dvalue, const float *dret, float *dpre, float *dWp, float *dWv, float *dWr, float *dbias_p,
+                  float *dbias_v, float *dbias_r, float *workspace, void *stream);
+
+/*
  * Weight of a stride-1 "same" convolution (Cout,Cin,kh,kw; odd kernel, zero padding) <-> the dense matrix
  * (Cout*H*W, Cin*H*W) that applies it to an H x W board stored NCHW (fastnet.BoardConv2d), and the adjoint map
  * dense-gradient -> weight-gradient.  dense[(o,q),(i,p)] = w[o,i,a,b] where tap (a,b) makes output cell q read input
