@@ -31,11 +31,12 @@
 
 namespace hrl {
 
-constexpr int kGemmThreads = 512;
+constexpr int kGemmThreads = 512;          // producer / epilogue threads (16 warps)
+constexpr int kGemmBlock = kGemmThreads + 32;   // + one warp that only issues tcgen05.mma
 constexpr int kTileM = 128;
 constexpr int kMaxN = 288;          // columns of one CTA tile (TMEM: 512 fp32 columns; shared memory: 2 stages)
 constexpr int kChunkK = 32;         // reduction elements per shared-memory stage
-constexpr int kStages = 2;
+constexpr int kStages = 3;
 
 struct GemmOperand {
     const float *ptr, *ptr2;        // ptr2: optional second source with the same layout (operand = x*p + y*q + r), or NULL
@@ -208,14 +209,41 @@ __device__ __forceinline__ float4 transform_item(const GemmOperand &op, const It
     return v;
 }
 
+// tcgen05.mma with the A operand in tensor memory (lane = row, one 32-bit column per reduction element) and B in shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                 "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+
+constexpr int kAColBase = 288;      // TMEM columns: accumulator [0, 288), A stages [288 + 64 s, ...): 32 hi + 32 lo columns each
+
+// The A operand goes global -> registers -> (transform, hi/lo split) -> TENSOR MEMORY, the B operand -> shared memory
+// (SWIZZLE_128B).  Three 3xTF32 products per k-step then read only B from shared memory: with both operands in shared
+// memory the product was bound by shared-memory bandwidth (each tcgen05.mma re-read 4 KB of A and 4.6 KB of B every
+// 72 cycles while the producers wrote the next stage), see profiles/README.md.
+// A thread owns ONE row of the A tile (its TMEM lane: warp w may only touch lanes 32 (w % 4) ... + 31) and 8 of the 32
+// reduction elements of a chunk (warp group w / 4).
 template <bool A_K, bool B_K, int ITEMS_A, int ITEMS_B>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const GemmParams p, const int n_pad) {
+__global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmParams p, const int n_pad) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // swizzle atoms need 1024-byte alignment
-    __shared__ __align__(8) uint64_t bars[kStages + 1];
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 1];      // full[kStages] | empty[kStages] | accumulator done
     __shared__ uint32_t tmem_base_slot;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool issuer = warp == kGemmThreads / 32;
     const int m0 = blockIdx.x * kTileM;
     const int n0 = blockIdx.y * kMaxN;
     const int split = blockIdx.z;
@@ -225,13 +253,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
     const int c_begin = split * p.chunks_per_split;
     const int c_end = min(total_chunks, c_begin + p.chunks_per_split);
 
-    // stage layout: [A_hi | A_lo | B_hi | B_lo], each [rows][128 B] with the 16-byte slots of a row swizzled
-    const uint32_t a_bytes = kTileM * kChunkK * 4, b_bytes = (uint32_t)n_pad * kChunkK * 4;
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    // shared-memory stage: [B_hi | B_lo], each [rows][128 B] with the 16-byte slots of a row swizzled
+    const uint32_t b_bytes = (uint32_t)n_pad * kChunkK * 4;
+    const uint32_t stage_bytes = 2 * b_bytes;
     const uint32_t smem_base = smem_u32(smem);
 
     if (tid == 0) {
-        for (int s = 0; s <= kStages; s++) mbar_init(smem_u32(&bars[s]), 1);
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(smem_u32(&bars[s]), kGemmThreads);             // full: every producer thread arrives
+            mbar_init(smem_u32(&bars[kStages + s]), 1);              // empty: one tcgen05.commit
+        }
+        mbar_init(smem_u32(&bars[2 * kStages]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -244,40 +276,111 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
 
-    const long long off_a = A_K ? (long long)m0 * p.a.ld : (long long)m0;
-    const long long off_b = B_K ? (long long)n0 * p.b.ld : (long long)n0;
-    const float *Ag = p.a.ptr + off_a;
-    const float *Bg = p.b.ptr + off_b;
-    const long long a2 = p.a.ptr2 ? (p.a.ptr2 - p.a.ptr) : 0, b2 = p.b.ptr2 ? (p.b.ptr2 - p.b.ptr) : 0;   // second sources
+    // ---- A: this thread's row and 8-element slice of every chunk
+    const int a_q = warp & 3, a_g = warp >> 2;
+    const int a_row = a_q * 32 + lane;                   // row of the tile == TMEM lane
+    const bool a_live = a_row < rows_a;
+    const int a_k = 8 * a_g;                             // offset of the slice inside a chunk
+    const float *a_ptr = p.a.ptr + (A_K ? (long long)(m0 + a_row) * p.a.ld + a_k : (long long)a_k * p.a.ld + (m0 + a_row));
+    const long long a2 = p.a.ptr2 ? (p.a.ptr2 - p.a.ptr) : 0;
     const bool vec_a = A_K && (p.a.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a.ptr) & 15) == 0) &&
                        (!p.a.ptr2 || (reinterpret_cast<uintptr_t>(p.a.ptr2) & 15) == 0);
+    float a_pr = 1.f, a_qr = 0.f, a_rr = 0.f;            // per-row transform constants
+    if (p.a.p != nullptr && p.a.feature_is_row && a_live) {
+        a_pr = __ldg(p.a.p + m0 + a_row);
+        a_rr = __ldg(p.a.r + m0 + a_row);
+        if (p.a.q != nullptr) a_qr = __ldg(p.a.q + m0 + a_row);
+    }
+    const uint32_t a_taddr = tmem_base + ((uint32_t)(a_q * 32) << 16) + kAColBase + a_k;
+
+    // ---- B: items as before
+    const long long off_b = B_K ? (long long)n0 * p.b.ld : (long long)n0;
+    const float *Bg = p.b.ptr + off_b;
+    const long long b2 = p.b.ptr2 ? (p.b.ptr2 - p.b.ptr) : 0;
     const bool vec_b = B_K && (p.b.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.b.ptr) & 15) == 0) &&
                        (!p.b.ptr2 || (reinterpret_cast<uintptr_t>(p.b.ptr2) & 15) == 0);
     const int halves = n_pad > 256 ? 2 : 1;
     const int n_mma = n_pad / halves;
     const uint32_t idesc = umma_idesc_tf32(kTileM, n_mma);
-
-    Item ia[ITEMS_A], ib[ITEMS_B];
-#pragma unroll
-    for (int u = 0; u < ITEMS_A; u++) ia[u] = make_item<A_K>(tid + u * kGemmThreads, kTileM * 8, Ag, p.a.ld, kTileM, rows_a, m0);
+    Item ib[ITEMS_B];
 #pragma unroll
     for (int u = 0; u < ITEMS_B; u++) ib[u] = make_item<B_K>(tid + u * kGemmThreads, n_pad * 8, Bg, p.b.ld, n_pad, n_here, n0);
 
+    if (issuer) {
+        // ---- the MMA warp: waits for a stage to be full, issues its 3 x 4 (x halves) products, commits them to the
+        //      stage's "empty" barrier (and the last ones to the accumulator barrier).  It never touches operand data.
+        for (int c = c_begin; c < c_end; c++) {
+            const int it = c - c_begin, s = it % kStages;
+            mbar_wait(smem_u32(&bars[s]), (it / kStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                if (p.debug != 1) {
+                    const uint32_t st = smem_base + s * stage_bytes;
+                    const uint32_t b_hi = st, b_lo = st + b_bytes;
+                    const uint32_t a_hi = tmem_base + kAColBase + 64 * s, a_lo = a_hi + 32;
+#pragma unroll
+                    for (int ks = 0; ks < kChunkK / 8; ks++) {
+                        for (int h = 0; h < halves; h++) {
+                            const uint32_t boff = 32 * ks + h * n_mma * 128;      // n_mma % 8 == 0: whole swizzle atoms
+                            const uint32_t d = tmem_base + h * n_mma;
+                            const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
+                            // small terms first: a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
+                            umma_tf32_ts(d, a_lo + 8 * ks, umma_desc(b_hi + boff), idesc, first);
+                            umma_tf32_ts(d, a_hi + 8 * ks, umma_desc(b_lo + boff), idesc, 1u);
+                            umma_tf32_ts(d, a_hi + 8 * ks, umma_desc(b_hi + boff), idesc, 1u);
+                        }
+                    }
+                }
+                umma_commit(smem_u32(&bars[kStages + s]));
+                if (c == c_end - 1) umma_commit(smem_u32(&bars[2 * kStages]));
+            }
+            __syncwarp();
+        }
+    } else
     for (int c = c_begin; c < c_end; c++) {
-        const int it = c - c_begin, s = it & 1;
+        const int it = c - c_begin, s = it % kStages;
         const int k0 = c * kChunkK;
         const int k_left = p.K - k0;
         const long long adv_a = A_K ? (long long)k0 : (long long)k0 * p.a.ld;
         const long long adv_b = B_K ? (long long)k0 : (long long)k0 * p.b.ld;
         // ---- global loads of this chunk (issued before waiting for the stage: latency overlaps the running MMAs)
-        float4 va[ITEMS_A], vb[ITEMS_B];
+        float xa[8], ya[8];
+        float4 vb[ITEMS_B];
         if (p.debug != 2) {
 #pragma unroll
-            for (int u = 0; u < ITEMS_A; u++) {
-                va[u] = load_item<A_K>(ia[u], p.a.ld, vec_a, adv_a, k_left);
+            for (int e = 0; e < 8; e++) xa[e] = ya[e] = 0.f;
+            if (a_live) {
+                const float *q = a_ptr + adv_a;
+                if (A_K && vec_a && a_k + 7 < k_left) {
+                    const float4 u0 = __ldg(reinterpret_cast<const float4 *>(q)), u1 = __ldg(reinterpret_cast<const float4 *>(q) + 1);
+                    xa[0] = u0.x; xa[1] = u0.y; xa[2] = u0.z; xa[3] = u0.w; xa[4] = u1.x; xa[5] = u1.y; xa[6] = u1.z; xa[7] = u1.w;
+                    if (p.a.ptr2) {
+                        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(q + a2)), w1 = __ldg(reinterpret_cast<const float4 *>(q + a2) + 1);
+                        ya[0] = w0.x; ya[1] = w0.y; ya[2] = w0.z; ya[3] = w0.w; ya[4] = w1.x; ya[5] = w1.y; ya[6] = w1.z; ya[7] = w1.w;
+                    }
+                } else {
+                    const long long st = A_K ? 1 : p.a.ld;
+#pragma unroll
+                    for (int e = 0; e < 8; e++)
+                        if (a_k + e < k_left) {
+                            xa[e] = __ldg(q + e * st);
+                            if (p.a.ptr2) ya[e] = __ldg(q + a2 + e * st);
+                        }
+                }
                 if (p.a.p != nullptr) {
-                    const float4 y = p.a.ptr2 ? load_item<A_K>(ia[u], p.a.ld, vec_a, adv_a + a2, k_left) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    va[u] = transform_item(p.a, ia[u], va[u], y, k0, k_left);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        if (a_k + e < k_left) {
+                            float pp = a_pr, qq = a_qr, rr = a_rr;
+                            if (!p.a.feature_is_row) {      // constants indexed by the reduction index: uniform over the warp
+                                pp = __ldg(p.a.p + k0 + a_k + e);
+                                rr = __ldg(p.a.r + k0 + a_k + e);
+                                qq = p.a.q ? __ldg(p.a.q + k0 + a_k + e) : 0.f;
+                            }
+                            float v = fmaf(xa[e], pp, fmaf(ya[e], qq, rr));
+                            xa[e] = p.a.relu ? fmaxf(v, 0.f) : v;
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -289,52 +392,31 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
                 }
             }
         }
-        if (it >= kStages) mbar_wait(smem_u32(&bars[s]), ((it >> 1) - 1) & 1);      // the MMAs that read this stage are done
+        if (it >= kStages) mbar_wait(smem_u32(&bars[kStages + s]), ((it / kStages) - 1) & 1);      // the MMAs that read this stage are done
         if (p.debug != 2) {
-            uint8_t *stp = smem + s * stage_bytes;
+            float hi[8], lo[8];
 #pragma unroll
-            for (int u = 0; u < ITEMS_A; u++) {
-                float4 hi, lo;
-                split_tf32(va[u], hi, lo);
-                *reinterpret_cast<float4 *>(stp + ia[u].slot) = hi;
-                *reinterpret_cast<float4 *>(stp + a_bytes + ia[u].slot) = lo;
+            for (int e = 0; e < 8; e++) {
+                hi[e] = __uint_as_float(__float_as_uint(xa[e]) & 0xFFFFE000u);
+                lo[e] = xa[e] - hi[e];
             }
+            tmem_st8(a_taddr + 64 * s, hi);
+            tmem_st8(a_taddr + 64 * s + 32, lo);
+            uint8_t *stp = smem + s * stage_bytes;
 #pragma unroll
             for (int u = 0; u < ITEMS_B; u++) {
                 if (ib[u].slot != 0xFFFFFFFFu) {
-                    float4 hi, lo;
-                    split_tf32(vb[u], hi, lo);
-                    *reinterpret_cast<float4 *>(stp + 2 * a_bytes + ib[u].slot) = hi;
-                    *reinterpret_cast<float4 *>(stp + 2 * a_bytes + b_bytes + ib[u].slot) = lo;
+                    float4 h4, l4;
+                    split_tf32(vb[u], h4, l4);
+                    *reinterpret_cast<float4 *>(stp + ib[u].slot) = h4;
+                    *reinterpret_cast<float4 *>(stp + b_bytes + ib[u].slot) = l4;
                 }
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        const uint32_t st = smem_base + s * stage_bytes;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
-        __syncthreads();
-        if (tid == 0 && p.debug == 1) {
-            umma_commit(smem_u32(&bars[s]));
-            if (c == c_end - 1) umma_commit(smem_u32(&bars[kStages]));
-        }
-        if (tid == 0 && p.debug != 1) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = st, a_lo = st + a_bytes, b_hi = st + 2 * a_bytes, b_lo = st + 2 * a_bytes + b_bytes;
-#pragma unroll
-            for (int ks = 0; ks < kChunkK / 8; ks++) {
-                for (int h = 0; h < halves; h++) {
-                    const uint32_t boff = 32 * ks + h * n_mma * 128;      // n_mma % 8 == 0: whole swizzle atoms
-                    const uint32_t aoff = 32 * ks;
-                    const uint32_t d = tmem_base + h * n_mma;
-                    const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
-                    // small terms first: a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
-                    umma_tf32(d, umma_desc(a_lo + aoff), umma_desc(b_hi + boff), idesc, first);
-                    umma_tf32(d, umma_desc(a_hi + aoff), umma_desc(b_lo + boff), idesc, 1u);
-                    umma_tf32(d, umma_desc(a_hi + aoff), umma_desc(b_hi + boff), idesc, 1u);
-                }
-            }
-            umma_commit(smem_u32(&bars[s]));
-            if (c == c_end - 1) umma_commit(smem_u32(&bars[kStages]));
-        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[s])) : "memory");      // this stage is full
     }
 
     // ---- epilogue: TMEM -> registers -> shared-memory tile (padded rows) -> coalesced global stores.
@@ -347,10 +429,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
     const int ldt = n_pad + 4;                           // row stride = 16 (mod 128) bytes: conflict-free 16-byte stores
     float *tile = reinterpret_cast<float *>(smem);       // the stages are free once the last MMAs have completed
     if (n_chunks_here > 0) {
-        mbar_wait(smem_u32(&bars[kStages]), 0);
+        mbar_wait(smem_u32(&bars[2 * kStages]), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    {
+    if (!issuer) {
         float *trow = tile + (q * 32 + (tid & 31)) * ldt;
         for (int cb = 0; cb < cols_per_group; cb += 8) {
             const int col = group * cols_per_group + cb;
@@ -378,13 +460,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
     __syncthreads();
     {
         // copy-out: a warp owns rows warp, warp+16, ...; a lane owns the float4 column groups lane, lane+32, lane+64.
+        // (the MMA warp has nothing to do here but takes part in the barriers)
         //   HRL_GEMM_EP_RELU        C = max(acc, 0)
         //   HRL_GEMM_EP_STATS       C = acc, plus per-column sum and sum of squares over the tile's rows
         //   HRL_GEMM_EP_MASK_STATS  C = acc * (z > 0) with z = y*scale+shift of the pre-activation tile y (the ReLU
         //                           backward), plus per-column sums of C and of C * xhat, xhat = (y - mean) * rstd
         //                           (the two batch sums the BatchNorm backward needs)
         const bool vec_c = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cg) & 15) == 0) && (n0 % 4 == 0) && (n_here % 4 == 0);
-        const int lane = tid & 31;
         const int ep = p.epilogue;
         const bool stats = (ep == HRL_GEMM_EP_STATS || ep == HRL_GEMM_EP_MASK_STATS) && p.col_partials != nullptr;
         constexpr int kGroupsPerLane = (kMaxN / 4 + 31) / 32;      // 3
@@ -393,8 +475,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
         for (int g = 0; g < kGroupsPerLane; g++)
 #pragma unroll
             for (int e = 0; e < 4; e++) s1[g][e] = s2[g][e] = 0.f;
-        if (vec_c && (ep == HRL_GEMM_EP_STORE || ep == HRL_GEMM_EP_RELU || ((ep == HRL_GEMM_EP_STATS || ep == HRL_GEMM_EP_MASK_STATS)))) {
+        if (issuer) {
+        } else if (vec_c) {
             const bool vec_y = ep == HRL_GEMM_EP_MASK_STATS && (p.ep_ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.ep_y) & 15) == 0);
+            // a lane always handles the same columns: their constants are loaded once, not per row
+            float k_sc[kGroupsPerLane][4], k_sh[kGroupsPerLane][4], k_mu[kGroupsPerLane][4], k_rs[kGroupsPerLane][4];
+            if (ep == HRL_GEMM_EP_MASK_STATS) {
+#pragma unroll
+                for (int g = 0; g < kGroupsPerLane; g++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int col = n0 + 4 * (lane + 32 * g) + e;
+                        const bool in = 4 * (lane + 32 * g) + e < n_here;
+                        k_sc[g][e] = (in && p.ep_scale) ? __ldg(p.ep_scale + col) : 1.f;
+                        k_sh[g][e] = (in && p.ep_shift) ? __ldg(p.ep_shift + col) : 0.f;
+                        k_mu[g][e] = (in && p.ep_mean) ? __ldg(p.ep_mean + col) : 0.f;
+                        k_rs[g][e] = (in && p.ep_rstd) ? __ldg(p.ep_rstd + col) : 1.f;
+                    }
+            }
             for (int r = warp; r < rows_a; r += kGemmThreads / 32) {
                 const float *src = tile + r * ldt;
                 float *dst = Cg + (long long)(m0 + r) * p.ldc + n0;
@@ -418,10 +516,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
                         float yv[4] = {y.x, y.y, y.z, y.w}, vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
-                            const float sc = p.ep_scale ? __ldg(p.ep_scale + col + e) : 1.f, sh = p.ep_shift ? __ldg(p.ep_shift + col + e) : 0.f;
-                            const float z = fmaf(yv[e], sc, sh);
+                            const float z = fmaf(yv[e], k_sc[g][e], k_sh[g][e]);
                             const float d = z > 0.f ? vv[e] : 0.f;
-                            const float xh = p.ep_mean ? (yv[e] - __ldg(p.ep_mean + col + e)) * __ldg(p.ep_rstd + col + e) : yv[e];
+                            const float xh = (yv[e] - k_mu[g][e]) * k_rs[g][e];
                             vv[e] = d;
                             s1[g][e] += d;
                             s2[g][e] = fmaf(d, xh, s2[g][e]);
@@ -444,7 +541,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
 #pragma unroll
             for (int g = 0; g < kGroupsPerLane; g++) {
                 const int c4 = lane + 32 * g;
-                if (c4 < n_pad / 4) {
+                if (c4 < n_pad / 4 && !issuer) {
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         red[(warp * 2 + 0) * n_pad + 4 * c4 + e] = s1[g][e];
@@ -453,7 +550,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
                 }
             }
             __syncthreads();
-            for (int i = tid; i < 2 * n_here; i += kGemmThreads) {
+            for (int i = tid; i < 2 * n_here && !issuer; i += kGemmThreads) {
                 const int which = i / n_here, col = i - which * n_here;
                 float acc = 0.f;
                 for (int w = 0; w < kGemmThreads / 32; w++) acc += red[(w * 2 + which) * n_pad + col];
@@ -547,7 +644,9 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
     } else {
         p.C = g.C; p.ldc = g.ldc; p.c_split_stride = 0;
     }
-    const size_t smem_bytes = 1024 + (size_t)kStages * (2 * (size_t)kTileM * kChunkK * 4 + 2 * (size_t)n_pad * kChunkK * 4);
+    size_t smem_bytes = 1024 + (size_t)kStages * (2 * (size_t)n_pad * kChunkK * 4);
+    const size_t ep_bytes = 1024 + ((size_t)kTileM * (n_pad + 4) + 32 * (size_t)n_pad) * 4;      // epilogue tile + column-sum scratch
+    if (smem_bytes < ep_bytes) smem_bytes = ep_bytes;
     const dim3 grid((unsigned)((M + kTileM - 1) / kTileM), (unsigned)n_tiles, (unsigned)splits);
     const int items_b = (n_pad * 8 + kGemmThreads - 1) / kGemmThreads;
     constexpr int IA = kTileM * 8 / kGemmThreads;
@@ -555,7 +654,7 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
     {                                                                                                                     \
         HRL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<AK, BK, IA, IB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                             (int)smem_bytes));                                                            \
-        gemm_tf32x3_kernel<AK, BK, IA, IB><<<grid, kGemmThreads, smem_bytes, stream>>>(p, n_pad);                          \
+        gemm_tf32x3_kernel<AK, BK, IA, IB><<<grid, kGemmBlock, smem_bytes, stream>>>(p, n_pad);                          \
     }
 #define HRL_GEMM_LAUNCH(IB)                                                                    \
     {                                                                                         \
