@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-MAX_CELLS = 49            # BatchNorm: fused reductions up to 7x7 boards
+MAX_CELLS = 256           # BatchNorm: fused coalesced passes for boards up to 16x16 (NCHW or channels-last)
 DENSE_MAX_CELLS = 16      # convolution as a dense product: only while the board is about as small as the kernel
 DENSE_MAX_ELEMS = 1 << 20   # ... and the dense matrix stays small (4 MB)
 
@@ -93,7 +93,7 @@ class BoardConv2d(nn.Conv2d):
         HW = H * W
         Cout = self.out_channels
         BoardConv2d.dense_calls += 1
-        if x.is_cuda and x.dtype == torch.float32:
+        if x.is_cuda and x.dtype == torch.float32 and getattr(self, 'tensor_cores', True):
             # tensor cores: dense matrix by one kernel, then forward / input-gradient / weight-gradient as tcgen05 products
             from . import ops
             y = ops.board_conv(x, self.weight)
@@ -121,7 +121,7 @@ class BoardBatchNorm2d(nn.BatchNorm2d):
         N, C, H, W = x.shape
         if self.momentum is None:
             raise NotImplementedError('cumulative moving average BatchNorm is not rewritten')
-        if x.is_cuda and x.dtype == torch.float32 and self.affine and x.is_contiguous():
+        if x.is_cuda and x.dtype == torch.float32 and self.affine:
             # fused kernels (csrc/bn_kernel.cu): 3 coalesced passes forward, 3 backward
             from . import ops
             with torch.no_grad():
@@ -172,12 +172,16 @@ def _fused_cell_class(cls):
     return _CELL_CLASSES[cls]
 
 
-def optimize_small_boards(model):
-    """Swap eligible modules to their board-aware subclasses, in place.  Returns how many were swapped."""
+def optimize_small_boards(model, tensor_cores=True):
+    """Swap eligible modules to their board-aware subclasses, in place.  Returns how many were swapped.
+    tensor_cores=False keeps the dense products on cuBLAS fp32 SIMT kernels (bit-for-bit fp32 summation; the tensor-core
+    3xTF32 products truncate their fp32 accumulator and are ~1e-5 relative per product)."""
     n = 0
     for m in model.modules():
         if type(m) in _SWAPS:
             m.__class__ = _SWAPS[type(m)]
+            if isinstance(m, BoardConv2d):
+                m.__dict__['tensor_cores'] = bool(tensor_cores)
             n += 1
         elif _is_conv_lstm_cell(m) and not hasattr(type(m), '_hrl_original'):
             m.__class__ = _fused_cell_class(type(m))

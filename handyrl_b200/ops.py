@@ -483,34 +483,45 @@ def hidden_blend(h, nh, om):
     return _HiddenBlend.apply(h, nh, om)
 
 
+def _nchw_or_nhwc(x):
+    """(tensor in one of the two dense layouts, channels_last flag)"""
+    if x.is_contiguous():
+        return x, 0
+    if x.is_contiguous(memory_format=torch.channels_last):
+        return x, 1
+    return x.contiguous(), 0
+
+
 class _BatchNormTrain(torch.autograd.Function):
-    """nn.BatchNorm2d (training mode) on (N, C, H, W) with a small board, through hrl_bn_train_fwd / _bwd."""
+    """nn.BatchNorm2d (training mode) on (N, C, H, W) activations in NCHW or channels-last memory, through hrl_bn_train_fwd / _bwd."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum):
-        x = x.contiguous()
+        x, cl = _nchw_or_nhwc(x)
         N, Cn, H, W = x.shape
-        y = torch.empty_like(x)
+        y = torch.empty_like(x)          # keeps the memory format
         mean = torch.empty(Cn, dtype=torch.float32, device=x.device)
         rstd = torch.empty_like(mean)
-        ws = torch.empty(lib().hrl_bn_workspace_floats(N, Cn, H * W), dtype=torch.float32, device=x.device)
+        ws = torch.empty(lib().hrl_bn_workspace_floats(N, Cn, H * W, cl), dtype=torch.float32, device=x.device)
         check(lib().hrl_bn_train_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(running_mean),
-                                     _ptr(running_var), N, Cn, H * W, float(eps), float(momentum), _ptr(ws), _stream_ptr()))
+                                     _ptr(running_var), N, Cn, H * W, cl, float(eps), float(momentum), _ptr(ws), _stream_ptr()))
         _count(3)
         ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.cl = cl
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, weight, mean, rstd = ctx.saved_tensors
-        dy = dy.contiguous()
+        cl = ctx.cl
+        dy = dy.contiguous(memory_format=torch.channels_last) if cl else dy.contiguous()
         N, Cn, H, W = x.shape
         dx = torch.empty_like(x)
         dgamma = torch.empty(Cn, dtype=torch.float32, device=x.device)
         dbeta = torch.empty_like(dgamma)
-        ws = torch.empty(lib().hrl_bn_workspace_floats(N, Cn, H * W), dtype=torch.float32, device=x.device)
+        ws = torch.empty(lib().hrl_bn_workspace_floats(N, Cn, H * W, cl), dtype=torch.float32, device=x.device)
         check(lib().hrl_bn_train_bwd(_ptr(x), _ptr(dy), _ptr(weight), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
-                                     N, Cn, H * W, _ptr(ws), _stream_ptr()))
+                                     N, Cn, H * W, cl, _ptr(ws), _stream_ptr()))
         _count(3)
         return dx, (dgamma if weight is not None else None), (dbeta if ctx.needs_input_grad[2] else None), None, None, None, None
 

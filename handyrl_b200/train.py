@@ -338,7 +338,7 @@ class LearnerStep:
 
     def __init__(self, model, args, example_batch, lr, device=None, process_group=None, use_graph=True,
                  max_norm=4.0, weight_decay=1e-5, time_loss_kernel=False, channels_last=True, cudnn_benchmark=True,
-                 small_boards=True, peer_allreduce=None, allow_tf32=None, fused_tower=True):
+                 small_boards=True, peer_allreduce=None, allow_tf32=None, fused_tower=True, tensor_cores=None):
         self.device = torch.device(device if device is not None else 'cuda')
         self.args = args
         # the learner owns its precision contract (1e-5 of the reference's fp32 arithmetic): PyTorch's default lets
@@ -353,7 +353,12 @@ class LearnerStep:
         # implicit-GEMM kernels on the tiny boards of these games; NHWC + autotune is a pure layout choice
         # tiny boards: convolutions as one SGEMM, BatchNorm as fused reductions (fastnet.py); NCHW stays as is
         self.engine = None          # hand-scheduled fused forward/backward for recognised architectures (tower.py)
-        self.rewritten = fastnet.optimize_small_boards(self.model) if small_boards else 0
+        # train_args['tensor_cores'] = False: the small-board dense products stay on fp32 SIMT kernels (strict fp32 summation)
+        if tensor_cores is None:
+            tensor_cores = bool(args.get('tensor_cores', True))
+        self.tensor_cores = tensor_cores
+        fused_tower = fused_tower and tensor_cores
+        self.rewritten = fastnet.optimize_small_boards(self.model, tensor_cores=tensor_cores) if small_boards else 0
         if self.rewritten and channels_last:
             channels_last = not self._uses_dense_convs(example_batch)       # dense products want NCHW-flat activations
         self.memory_format = torch.channels_last if channels_last else None

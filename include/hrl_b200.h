@@ -320,14 +320,16 @@ int hrl_hidden_blend_bwd(const float *dout, const float *om, int64_t om_stride, 
  * net (the nets of reference envs normalise (N,32,3,3) / (N,C,6,6) tensors; cuDNN / ATen launch one CTA per channel
  * there).  Semantics of nn.BatchNorm2d in training mode: biased variance for the normalisation, unbiased for
  * running_var, running stats updated with `momentum` (pass NULL for both to skip).  mean / rstd (C floats each) are
- * saved for the backward.  workspace: hrl_bn_workspace_floats(N, C, HW) floats.
+ * saved for the backward.  channels_last = 1: x / y / dy / dx are (N, H, W, C) in memory (torch.channels_last), e.g. the
+ * activations between cuDNN's NHWC convolutions.  workspace: hrl_bn_workspace_floats(N, C, HW, channels_last) floats.
  */
-size_t hrl_bn_workspace_floats(int64_t N, int32_t C, int32_t HW);
+size_t hrl_bn_workspace_floats(int64_t N, int32_t C, int32_t HW, int32_t channels_last);
 int hrl_bn_train_fwd(const float *x, const float *gamma, const float *beta, float *y, float *mean, float *rstd,
-                     float *running_mean, float *running_var, int64_t N, int32_t C, int32_t HW, float eps, float momentum,
+                     float *running_mean, float *running_var, int64_t N, int32_t C, int32_t HW, int32_t channels_last, float eps, float momentum,
                      float *workspace, void *stream);
 int hrl_bn_train_bwd(const float *x, const float *dy, const float *gamma, const float *mean, const float *rstd, float *dx,
-                     float *dgamma, float *dbeta, int64_t N, int32_t C, int32_t HW, float *workspace, void *stream);
+                     float *dgamma, float *dbeta, int64_t N, int32_t C, int32_t HW, int32_t channels_last, float *workspace,
+                     void *stream);
 
 /*
  * Replay gather/pad: the device form of make_batch (train.py:33-124).

@@ -82,9 +82,11 @@ def test_peer_allreduce_kernel_world1_matches_sumsq():
         assert abs(float(partials.double().sum()) - want) <= 1e-5 * want
 
 
-@pytest.mark.parametrize('shape', [(16384, 32, 3, 3), (1000, 8, 6, 6), (37, 5, 4, 5)])
-def test_fused_batchnorm_matches_torch(shape):
-    """hrl_bn_train_fwd / _bwd vs nn.BatchNorm2d in training mode: output, input/affine gradients, running statistics."""
+@pytest.mark.parametrize('channels_last', [False, True], ids=['nchw', 'nhwc'])
+@pytest.mark.parametrize('shape', [(16384, 32, 3, 3), (1000, 8, 6, 6), (37, 5, 4, 5), (520, 32, 7, 11)])
+def test_fused_batchnorm_matches_torch(shape, channels_last):
+    """hrl_bn_train_fwd / _bwd vs nn.BatchNorm2d in training mode: output, input/affine gradients, running statistics,
+    for NCHW and channels-last activations (the layout between cuDNN's NHWC convolutions; 7x11 = the Hungry Geese board)."""
     from handyrl_b200 import fastnet
     torch.manual_seed(0)
     N, C, H, W = shape
@@ -98,10 +100,13 @@ def test_fused_batchnorm_matches_torch(shape):
     old = torch.backends.cudnn.enabled
     for it in range(2):
         x = (torch.randn(shape, device='cuda') * 2 + 0.5)
-        xr, xf = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
         g = torch.randn(shape, device='cuda')
+        if channels_last:
+            x, g = x.contiguous(memory_format=torch.channels_last), g.contiguous(memory_format=torch.channels_last)
+        xr, xf = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
         yr = ref(xr)
         yf = fast(xf)
+        assert yf.is_contiguous(memory_format=torch.channels_last if channels_last else torch.contiguous_format)
         yr.backward(g)
         yf.backward(g)
         torch.testing.assert_close(yf, yr, rtol=1e-5, atol=2e-5)

@@ -63,6 +63,31 @@ def test_three_learner_steps_match_reference_geister_and_geese_nets(name, use_gr
             assert int(v) == int(vr)
 
 
+@pytest.mark.parametrize('name', sorted(STEP_CASES))
+def test_three_learner_steps_strict_fp32_mode(name):
+    """train_args['tensor_cores'] = False: the net's products stay on fp32 SIMT kernels; the reference's three optimiser steps
+    are reproduced to the tolerances of plain fp32 reordering."""
+    from handyrl_b200.nets import tictactoe_net, load_state_by_order
+    from handyrl_b200.synthetic import synthetic_batch
+    from handyrl_b200.train import LearnerStep
+    c = STEP_CASES[name]
+    B, T, P, A = c['dims']
+    args = dict(c['args'], tensor_cores=False)
+    net = load_state_by_order(tictactoe_net(), c['state0'])
+    mk = lambda s: synthetic_batch(B, T, P, A, turn_based=args['turn_based_training'], observation=args['observation'], seed=40 + s)
+    stepper = LearnerStep(net, args, mk(0), lr=c['lr'])
+    assert stepper.engine is None and not stepper.tensor_cores
+    for s, ref in enumerate(c['steps']):
+        stepper.step(stepper.new_packed().fill(mk(s)))
+        got = stepper.read_losses()
+        for k, v in ref['losses'].items():
+            assert abs(got[k] - v) <= 2e-5 * abs(v) + 2e-5, (s, k, got[k], v)
+        assert abs(float(stepper.opt.grad_norm) - ref['grad_norm']) <= 1e-4 * ref['grad_norm']
+    for (k, v), (kr, vr) in zip(stepper.cpu_state_dict().items(), c['state3'].items()):
+        if v.dtype.is_floating_point:
+            np.testing.assert_allclose(v.numpy(), vr, rtol=1e-4, atol=2e-5, err_msg='%s/%s' % (k, kr))
+
+
 @pytest.mark.parametrize('use_graph', [False, True], ids=['eager', 'graph'])
 @pytest.mark.parametrize('name', sorted(STEP_CASES))
 def test_three_learner_steps_match_reference(name, use_graph):
