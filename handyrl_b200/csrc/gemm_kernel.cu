@@ -368,16 +368,36 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
                         }
                 }
                 if (p.a.p != nullptr) {
+                    float pp[8], qq[8], rr[8];
+                    if (p.a.feature_is_row) {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) { pp[e] = a_pr; qq[e] = a_qr; rr[e] = a_rr; }
+                    } else if (a_k + 7 < k_left) {      // constants of this warp's 8 reduction indices: uniform over the warp, vector loads
+                        const int f = k0 + a_k;
+                        const float4 p0 = __ldg(reinterpret_cast<const float4 *>(p.a.p + f)), p1 = __ldg(reinterpret_cast<const float4 *>(p.a.p + f) + 1);
+                        const float4 r0 = __ldg(reinterpret_cast<const float4 *>(p.a.r + f)), r1 = __ldg(reinterpret_cast<const float4 *>(p.a.r + f) + 1);
+                        pp[0] = p0.x; pp[1] = p0.y; pp[2] = p0.z; pp[3] = p0.w; pp[4] = p1.x; pp[5] = p1.y; pp[6] = p1.z; pp[7] = p1.w;
+                        rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+                        if (p.a.q) {
+                            const float4 q0 = __ldg(reinterpret_cast<const float4 *>(p.a.q + f)), q1 = __ldg(reinterpret_cast<const float4 *>(p.a.q + f) + 1);
+                            qq[0] = q0.x; qq[1] = q0.y; qq[2] = q0.z; qq[3] = q0.w; qq[4] = q1.x; qq[5] = q1.y; qq[6] = q1.z; qq[7] = q1.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; e++) qq[e] = 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            const bool in = a_k + e < k_left;
+                            pp[e] = in ? __ldg(p.a.p + k0 + a_k + e) : 0.f;
+                            rr[e] = in ? __ldg(p.a.r + k0 + a_k + e) : 0.f;
+                            qq[e] = (in && p.a.q) ? __ldg(p.a.q + k0 + a_k + e) : 0.f;
+                        }
+                    }
 #pragma unroll
                     for (int e = 0; e < 8; e++) {
                         if (a_k + e < k_left) {
-                            float pp = a_pr, qq = a_qr, rr = a_rr;
-                            if (!p.a.feature_is_row) {      // constants indexed by the reduction index: uniform over the warp
-                                pp = __ldg(p.a.p + k0 + a_k + e);
-                                rr = __ldg(p.a.r + k0 + a_k + e);
-                                qq = p.a.q ? __ldg(p.a.q + k0 + a_k + e) : 0.f;
-                            }
-                            float v = fmaf(xa[e], pp, fmaf(ya[e], qq, rr));
+                            const float v = fmaf(xa[e], pp[e], fmaf(ya[e], qq[e], rr[e]));
                             xa[e] = p.a.relu ? fmaxf(v, 0.f) : v;
                         }
                     }

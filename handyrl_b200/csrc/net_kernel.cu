@@ -33,11 +33,14 @@ __global__ void board_expand_kernel(const float *__restrict__ w, float *__restri
 // summed over the slices with coalesced reads (fixed order -> deterministic) into shared memory, then folded onto the taps
 __global__ void board_fold_kernel(const float *__restrict__ ddense, int splits, long long split_stride, float *__restrict__ dw, int Cout,
                                   int Cin, int kh, int kw, int H, int W) {
-    extern __shared__ float slab[];                   // [HW][Cin*HW]
+    extern __shared__ float slab[];                   // [HW][Cin*HW]; a CTA fills only the columns of its input channels
     const int HW = H * W, cols = Cin * HW, n = HW * cols;
     const int o = blockIdx.x;
+    const int i_per = (Cin + gridDim.y - 1) / gridDim.y, i_lo = blockIdx.y * i_per, i_hi = min(Cin, i_lo + i_per);
+    const int c_lo = i_lo * HW, c_n = (i_hi - i_lo) * HW;          // this CTA's column range
     const float *base = ddense + (long long)o * n;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    for (int e0 = threadIdx.x; e0 < HW * c_n; e0 += blockDim.x) {
+        const int e = (e0 / c_n) * cols + c_lo + e0 % c_n;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int sp = 0;
         for (; sp + 8 <= splits; sp += 8) {           // eight independent loads in flight per thread (latency-bound otherwise)
@@ -49,8 +52,8 @@ __global__ void board_fold_kernel(const float *__restrict__ ddense, int splits, 
     }
     __syncthreads();
     const int taps = kh * kw;
-    for (int t = threadIdx.x; t < Cin * taps; t += blockDim.x) {
-        const int i = t / taps, a = (t % taps) / kw, b = t % kw;
+    for (int t = threadIdx.x; t < (i_hi - i_lo) * taps; t += blockDim.x) {
+        const int i = i_lo + t / taps, a = (t % taps) / kw, b = t % kw;
         float s = 0.f;
         for (int qy = 0; qy < H; qy++) {
             const int py = qy + a - kh / 2;
@@ -207,8 +210,10 @@ extern "C" int hrl_board_fold(const float *ddense, int32_t splits, int64_t split
                 slab_bytes / sizeof(float));
     if (slab_bytes > 48 * 1024)
         HRL_CUDA_CHECK(cudaFuncSetAttribute(board_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab_bytes));
-    board_fold_kernel<<<Cout, 1024, slab_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(ddense, splits, split_stride, dw, Cout, Cin, kh, kw,
-                                                                                         H, W);
+    int groups = (2 * kNumSM + Cout - 1) / Cout;       // (output channel, group of input channels) CTAs: about two per SM
+    if (groups > Cin) groups = Cin;
+    board_fold_kernel<<<dim3(Cout, groups), 512, slab_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(ddense, splits, split_stride, dw, Cout,
+                                                                                                    Cin, kh, kw, H, W);
     HRL_CUDA_CHECK(cudaGetLastError());
     return HRL_OK;
 }

@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(128) heads_fwd_kernel(const float *__restrict_
 
 // backward: dpre (M, ld) and per-block partial sums of the parameter gradients:
 //   [dWp (A*pin) | dWv (vin) | dWr (rin) | dbias per squeeze map (pin+vin+rin)/cells]
+// phase 1: a thread per row writes dpre and leaves its activated squeeze outputs h, its dpre and its head gradients in
+// shared memory; phase 2: a thread per OUTPUT sums its 128 row products from there (fixed order, no shuffle trees).
 __global__ void __launch_bounds__(128) heads_bwd_kernel(const float *__restrict__ pre, long long ld, long long M, HeadsDims d, float slope,
                                                         const float *__restrict__ Wp, const float *__restrict__ Wv,
                                                         const float *__restrict__ Wr, const float *__restrict__ value,
@@ -140,57 +142,64 @@ __global__ void __launch_bounds__(128) heads_bwd_kernel(const float *__restrict_
                                                         const float *__restrict__ dret, float *__restrict__ dpre,
                                                         float *__restrict__ partials, int n_out) {
     __shared__ float sWp[kHeadMaxA * kHeadMaxIn], sWv[kHeadMaxIn], sWr[kHeadMaxIn];
-    extern __shared__ float acc[];                 // [4 warps][n_out]
+    extern __shared__ float sh[];                  // h [nin][129] | g [nin][129] | dp [A+2][129]   (row index fastest, padded)
+    constexpr int S = 129;
+    const int nin = d.pin + d.vin + d.rin;
+    float *sh_h = sh, *sh_g = sh + nin * S, *sh_d = sh + 2 * nin * S;
     for (int i = threadIdx.x; i < d.A * d.pin; i += blockDim.x) sWp[i] = Wp[i];
     for (int i = threadIdx.x; i < d.vin; i += blockDim.x) sWv[i] = Wv[i];
     for (int i = threadIdx.x; i < d.rin; i += blockDim.x) sWr[i] = Wr[i];
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tr = threadIdx.x;
+    const long long row = (long long)blockIdx.x * blockDim.x + tr;
     const bool live = row < M;
-    const int nin = d.pin + d.vin + d.rin;
     const float *x = pre + (live ? row : 0) * ld;
-    float *wacc = acc + warp * n_out;
     float dp[kHeadMaxA];
-    for (int a = 0; a < d.A; a++) dp[a] = live ? __ldg(dpolicy + row * d.A + a) : 0.f;
+    for (int a = 0; a < d.A; a++) {
+        dp[a] = live ? __ldg(dpolicy + row * d.A + a) : 0.f;
+        sh_d[a * S + tr] = dp[a];
+    }
     float dvp = 0.f, drp = 0.f;
     if (d.vin && live) { const float v = __ldg(value + row); dvp = __ldg(dvalue + row) * (1.f - v * v); }
     if (d.rin && live) drp = __ldg(dret + row);
-    int o_bias = d.A * d.pin + d.vin + d.rin;
-    float bias_acc = 0.f;
+    sh_d[d.A * S + tr] = dvp;
+    sh_d[(d.A + 1) * S + tr] = drp;
     for (int j = 0; j < nin; j++) {
         const float v = live ? __ldg(x + j) : 0.f;
-        const float h = v > 0.f ? v : v * slope;
         float g;                                   // gradient wrt the activated squeeze output j
         if (j < d.pin) {
             g = 0.f;
-            for (int a = 0; a < d.A; a++) {
-                g = fmaf(dp[a], sWp[a * d.pin + j], g);
-                const float t = warp_sum(dp[a] * h);
-                if (lane == 0) wacc[a * d.pin + j] = t;
-            }
+            for (int a = 0; a < d.A; a++) g = fmaf(dp[a], sWp[a * d.pin + j], g);
         } else if (j < d.pin + d.vin) {
             g = dvp * sWv[j - d.pin];
-            const float t = warp_sum(dvp * h);
-            if (lane == 0) wacc[d.A * d.pin + (j - d.pin)] = t;
         } else {
             g = drp * sWr[j - d.pin - d.vin];
-            const float t = warp_sum(drp * h);
-            if (lane == 0) wacc[d.A * d.pin + d.vin + (j - d.pin - d.vin)] = t;
         }
         const float gp = live ? g * (v > 0.f ? 1.f : slope) : 0.f;
         if (live) dpre[row * ld + j] = gp;
-        bias_acc += gp;
-        if ((j + 1) % d.cells == 0) {               // one squeeze map done: its bias gradient
-            const float t = warp_sum(bias_acc);
-            if (lane == 0) wacc[o_bias++] = t;
-            else o_bias++;
-            bias_acc = 0.f;
-        }
+        sh_h[j * S + tr] = live ? (v > 0.f ? v : v * slope) : 0.f;
+        sh_g[j * S + tr] = gp;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_out; i += blockDim.x)
-        partials[(long long)blockIdx.x * n_out + i] = (acc[i] + acc[n_out + i]) + (acc[2 * n_out + i] + acc[3 * n_out + i]);
+    const int n_w = d.A * d.pin + d.vin + d.rin;
+    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+        float s = 0.f;
+        if (o < n_w) {                              // a Linear weight: sum_rows (head gradient) * (activated input)
+            int grad_row, j;
+            if (o < d.A * d.pin) { grad_row = o / d.pin; j = o - grad_row * d.pin; }
+            else if (o < d.A * d.pin + d.vin) { grad_row = d.A; j = d.pin + (o - d.A * d.pin); }
+            else { grad_row = d.A + 1; j = d.pin + d.vin + (o - d.A * d.pin - d.vin); }
+            const float *gd = sh_d + grad_row * S, *hh = sh_h + j * S;
+            for (int r = 0; r < 128; r++) s = fmaf(gd[r], hh[r], s);
+        } else {                                    // a squeeze bias: sum over rows and the map's cells of dpre
+            const int map = o - n_w;
+            for (int cell = 0; cell < d.cells; cell++) {
+                const float *gg = sh_g + (map * d.cells + cell) * S;
+                for (int r = 0; r < 128; r++) s += gg[r];
+            }
+        }
+        partials[(long long)blockIdx.x * n_out + o] = s;
+    }
 }
 
 // out[i] = sum over blocks of partials[block][i] in a fixed order, scattered to up to 8 destination ranges
@@ -274,8 +283,10 @@ extern "C" int hrl_heads_bwd(const float *pre, int64_t ld, int64_t M, int32_t ce
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     const int n_out = A * d.pin + d.vin + d.rin + pmaps + vmaps + rmaps;
     const int blocks = hrl_heads_num_blocks(M);
-    heads_bwd_kernel<<<blocks, 128, (size_t)4 * n_out * sizeof(float), stream>>>(pre, ld, M, d, slope, Wp, Wv, Wr, value, dpolicy, dvalue, dret,
-                                                                                dpre, workspace, n_out);
+    const size_t sh_bytes = (size_t)(2 * (d.pin + d.vin + d.rin) + A + 2) * 129 * sizeof(float);
+    if (sh_bytes > 40 * 1024)
+        HRL_CUDA_CHECK(cudaFuncSetAttribute(heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes));
+    heads_bwd_kernel<<<blocks, 128, sh_bytes, stream>>>(pre, ld, M, d, slope, Wp, Wv, Wr, value, dpolicy, dvalue, dret, dpre, workspace, n_out);
     HRL_CUDA_CHECK(cudaGetLastError());
     ScatterPlan plan;
     int k = 0, at = 0;
