@@ -52,7 +52,7 @@ class HrlLossArgs(C.Structure):
 
 class HrlGemmOperand(C.Structure):
     _fields_ = [('ptr', C.c_void_p), ('ptr2', C.c_void_p), ('p', C.c_void_p), ('q', C.c_void_p), ('r', C.c_void_p),
-                ('ld', C.c_int64), ('kmajor', C.c_int32), ('relu', C.c_int32), ('feature_is_row', C.c_int32)]
+                ('ld', C.c_int64), ('kmajor', C.c_int32), ('relu', C.c_int32), ('feature_is_row', C.c_int32), ('packed', C.c_int32)]
 
 
 GEMM_EPILOGUES = {'store': 0, 'relu': 1, 'stats': 2, 'mask_stats': 3}
@@ -113,6 +113,9 @@ SYMBOLS = {
     'hrl_heads_num_blocks': (C.c_int32, [C.c_int64]),
     'hrl_heads_fwd': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_int32] * 5 + [C.c_float] + [C.c_void_p] * 7),
     'hrl_heads_bwd': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_int32] * 5 + [C.c_float] + [C.c_void_p] * 16),
+    'hrl_gemm_padded_rows': (C.c_int32, [C.c_int64]),
+    'hrl_board_pack_floats': (C.c_size_t, [C.c_int64, C.c_int64]),
+    'hrl_board_pack': (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'hrl_board_expand': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     'hrl_board_fold': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     'hrl_gemm_effective_splits': (C.c_int32, [C.c_int64, C.c_int32]),

@@ -45,6 +45,7 @@ struct GemmOperand {
     int kmajor;                     // 1: element (row,k) at row*ld + k ; 0: at k*ld + row
     int relu;                       // clamp the transformed operand at 0
     int feature_is_row;             // constants indexed by the operand's row (else by the reduction index k)
+    int packed;                     // B only: ptr is the hrl_board_pack image [chunk][hi|lo][n_pad rows][128 B swizzled]
 };
 
 struct GemmParams {
@@ -120,18 +121,24 @@ __device__ __forceinline__ void split_tf32(const float4 v, float4 &hi, float4 &l
     lo.w = v.w - hi.w;
 }
 
-// ---- operand loaders.  Every thread owns a fixed set of "items" (one row x 4 consecutive reduction elements = one 16-byte
-// shared-memory slot per split half); their coordinates are computed once, each chunk only advances the pointers.
-struct Item {
-    const float *ptr;      // first of the 4 elements in chunk 0 (valid rows only)
+// ---- B operand loaders.  Every thread owns a fixed set of "items" (one row x 4 consecutive reduction elements = one 16-byte
+// shared-memory slot per split half, K-major SWIZZLE_128B: a row's chunk = 128 bytes, slot j of row r at j ^ (r & 7)); their
+// coordinates are computed once, each chunk only advances the pointers.
+// (An operand stored [K][rows] is transposed by the loads -- 4 scalar loads per item, coalesced along the rows.  Staging it
+//  untransposed in the MN-major layout 32-bit operands have (SWIZZLE_128B_BASE32B, layout type 1, Swizzle<2,5,2> over 32 rows
+//  x 4 reduction elements, LBO 4096 / SBO 512) was tried: one vector load per item and correct results, but tcgen05.mma
+//  reads such an operand at 32-bit granularity and the product got 35% SLOWER, 42 -> 57 us at 288 x 288 x 16384 in 48 slices.)
+struct Item {              // three registers per item (a thread holds up to 5)
+    int off;               // first of the 4 elements in chunk 0, relative to the tile's first element
     uint32_t slot;         // byte offset of the 16-byte slot inside an operand half: row * 128 + ((j ^ (row & 7)) << 4)
-    int k;                 // 4 * j: offset of the quad inside a chunk
-    int row;               // operand row (for per-row transform constants)
-    bool live;             // the row exists
+    uint32_t meta;         // k | live << 9 | row << 10;  k = 4 * j: offset of the quad inside a chunk, row: for per-row constants
+    __device__ __forceinline__ int k() const { return (int)(meta & 63u); }
+    __device__ __forceinline__ bool live() const { return (meta >> 9) & 1u; }
+    __device__ __forceinline__ int row() const { return (int)(meta >> 10); }
 };
 
 template <bool KMAJOR>
-__device__ __forceinline__ Item make_item(int i, int n_items, const float *base, long long ld, int rows_pad, int rows, int row0) {
+__device__ __forceinline__ Item make_item(int i, int n_items, long long ld, int rows_pad, int rows, int row0) {
     Item it;
     int row, j;
     if (KMAJOR) {           // 8 consecutive lanes = the 128 contiguous bytes of one row's chunk: one cache line per quarter
@@ -141,21 +148,20 @@ __device__ __forceinline__ Item make_item(int i, int n_items, const float *base,
         j = i / rows_pad;   // spreads 8 consecutive rows of one slot column over 8 distinct slots
         row = i - j * rows_pad;
     }
-    it.live = i < n_items && row < rows;
-    it.k = 4 * j;
-    it.row = row0 + row;
+    const bool live = i < n_items && row < rows;
+    it.meta = (uint32_t)(4 * j) | ((live ? 1u : 0u) << 9) | ((uint32_t)(row0 + row) << 10);
     it.slot = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
-    it.ptr = base + (KMAJOR ? (long long)row * ld + 4 * j : (long long)(4 * j) * ld + row);
+    it.off = (int)(KMAJOR ? (long long)row * ld + 4 * j : (long long)(4 * j) * ld + row);
     if (i >= n_items) it.slot = 0xFFFFFFFFu;
     return it;
 }
 
 template <bool KMAJOR>
-__device__ __forceinline__ float4 load_item(const Item &it, long long ld, bool vec, long long advance, int k_left) {
+__device__ __forceinline__ float4 load_item(const Item &it, const float *base, long long ld, bool vec, long long advance, int k_left) {
     // k_left = reduction elements from this chunk's start to the end of the operand (>= 32 in every chunk but the last)
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!it.live) return v;
-    const float *q = it.ptr + advance;
+    if (!it.live()) return v;
+    const float *q = base + it.off + advance;
     if (k_left >= kChunkK) {                     // interior chunk: no per-element bounds
         if (KMAJOR) {
             if (vec) return __ldg(reinterpret_cast<const float4 *>(q));
@@ -166,34 +172,37 @@ __device__ __forceinline__ float4 load_item(const Item &it, long long ld, bool v
         return v;
     }
     const long long st = KMAJOR ? 1 : ld;          // last, partial chunk
-    if (it.k + 0 < k_left) v.x = __ldg(q);
-    if (it.k + 1 < k_left) v.y = __ldg(q + st);
-    if (it.k + 2 < k_left) v.z = __ldg(q + 2 * st);
-    if (it.k + 3 < k_left) v.w = __ldg(q + 3 * st);
+    const int k = it.k();
+    if (k + 0 < k_left) v.x = __ldg(q);
+    if (k + 1 < k_left) v.y = __ldg(q + st);
+    if (k + 2 < k_left) v.z = __ldg(q + 2 * st);
+    if (k + 3 < k_left) v.w = __ldg(q + 3 * st);
     return v;
 }
 
 // operand transform v = x*p[f] + y*q[f] + r[f] (relu optional) on the 4 elements of an item; elements outside the operand
-// (dead rows, reduction tail) stay exactly zero.  f = the operand row, or the reduction index k0 + it.k + e.
+// (dead rows, reduction tail) stay exactly zero.  f = the operand row, or the reduction index k0 + k + e.
 __device__ __forceinline__ float4 transform_item(const GemmOperand &op, const Item &it, float4 x, float4 y, int k0, int k_left) {
-    if (op.p == nullptr || !it.live) return x;
+    if (op.p == nullptr || !it.live()) return x;
     float4 pp, qq = make_float4(0.f, 0.f, 0.f, 0.f), rr;
+    const int k = it.k();
     if (op.feature_is_row) {
-        const float a = __ldg(op.p + it.row), c = __ldg(op.r + it.row);
+        const int row = it.row();
+        const float a = __ldg(op.p + row), c = __ldg(op.r + row);
         pp = make_float4(a, a, a, a);
         rr = make_float4(c, c, c, c);
-        if (op.q != nullptr) { const float bq = __ldg(op.q + it.row); qq = make_float4(bq, bq, bq, bq); }
+        if (op.q != nullptr) { const float bq = __ldg(op.q + row); qq = make_float4(bq, bq, bq, bq); }
     } else {
-        const int f = k0 + it.k;
-        if (it.k + 3 < k_left) {                   // k0 and it.k are multiples of 4: aligned vector loads of the constants
+        const int f = k0 + k;
+        if (k + 3 < k_left) {                      // k0 and k are multiples of 4: aligned vector loads of the constants
             pp = __ldg(reinterpret_cast<const float4 *>(op.p + f));
             rr = __ldg(reinterpret_cast<const float4 *>(op.r + f));
             if (op.q != nullptr) qq = __ldg(reinterpret_cast<const float4 *>(op.q + f));
         } else {
             pp = rr = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (it.k + 0 < k_left) { pp.x = __ldg(op.p + f); rr.x = __ldg(op.r + f); if (op.q) qq.x = __ldg(op.q + f); }
-            if (it.k + 1 < k_left) { pp.y = __ldg(op.p + f + 1); rr.y = __ldg(op.r + f + 1); if (op.q) qq.y = __ldg(op.q + f + 1); }
-            if (it.k + 2 < k_left) { pp.z = __ldg(op.p + f + 2); rr.z = __ldg(op.r + f + 2); if (op.q) qq.z = __ldg(op.q + f + 2); }
+            if (k + 0 < k_left) { pp.x = __ldg(op.p + f); rr.x = __ldg(op.r + f); if (op.q) qq.x = __ldg(op.q + f); }
+            if (k + 1 < k_left) { pp.y = __ldg(op.p + f + 1); rr.y = __ldg(op.r + f + 1); if (op.q) qq.y = __ldg(op.q + f + 1); }
+            if (k + 2 < k_left) { pp.z = __ldg(op.p + f + 2); rr.z = __ldg(op.r + f + 2); if (op.q) qq.z = __ldg(op.q + f + 2); }
         }
     }
     float4 v;
@@ -202,10 +211,10 @@ __device__ __forceinline__ float4 transform_item(const GemmOperand &op, const It
     v.z = fmaf(x.z, pp.z, fmaf(y.z, qq.z, rr.z));
     v.w = fmaf(x.w, pp.w, fmaf(y.w, qq.w, rr.w));
     if (op.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    if (it.k + 0 >= k_left) v.x = 0.f;
-    if (it.k + 1 >= k_left) v.y = 0.f;
-    if (it.k + 2 >= k_left) v.z = 0.f;
-    if (it.k + 3 >= k_left) v.w = 0.f;
+    if (k + 0 >= k_left) v.x = 0.f;
+    if (k + 1 >= k_left) v.y = 0.f;
+    if (k + 2 >= k_left) v.z = 0.f;
+    if (k + 3 >= k_left) v.w = 0.f;
     return v;
 }
 
@@ -235,12 +244,13 @@ constexpr int kAColBase = 288;      // TMEM columns: accumulator [0, 288), A sta
 // 72 cycles while the producers wrote the next stage), see profiles/README.md.
 // A thread owns ONE row of the A tile (its TMEM lane: warp w may only touch lanes 32 (w % 4) ... + 31) and 8 of the 32
 // reduction elements of a chunk (warp group w / 4).
-template <bool A_K, bool B_K, int ITEMS_A, int ITEMS_B>
+template <bool A_K, bool B_K, int ITEMS_A, int ITEMS_B, bool PACKED>
 __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmParams p, const int n_pad) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // swizzle atoms need 1024-byte alignment
     __shared__ __align__(8) uint64_t bars[2 * kStages + 1];      // full[kStages] | empty[kStages] | accumulator done
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float b_consts[2][kMaxN];     // per-row constants of a single-source B transform (no registers, no per-chunk loads)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool issuer = warp == kGemmThreads / 32;
@@ -260,11 +270,20 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
 
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) {
-            mbar_init(smem_u32(&bars[s]), kGemmThreads);             // full: every producer thread arrives
+            mbar_init(smem_u32(&bars[s]), kGemmThreads + (PACKED ? 1 : 0));   // full: every producer thread (+ the bulk copy's expect_tx)
             mbar_init(smem_u32(&bars[kStages + s]), 1);              // empty: one tcgen05.commit
         }
         mbar_init(smem_u32(&bars[2 * kStages]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // single-source transform with per-row constants (the weight gradient's activation operand)
+    const bool b_rows = !PACKED && p.b.p != nullptr && p.b.feature_is_row && p.b.ptr2 == nullptr;
+    if (b_rows) {
+        for (int i = tid; i < kMaxN; i += kGemmBlock) {
+            const bool in = i < min(kMaxN, p.N - blockIdx.y * kMaxN);
+            b_consts[0][i] = in ? __ldg(p.b.p + blockIdx.y * kMaxN + i) : 1.f;
+            b_consts[1][i] = in ? __ldg(p.b.r + blockIdx.y * kMaxN + i) : 0.f;
+        }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512)
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
     const uint32_t idesc = umma_idesc_tf32(kTileM, n_mma);
     Item ib[ITEMS_B];
 #pragma unroll
-    for (int u = 0; u < ITEMS_B; u++) ib[u] = make_item<B_K>(tid + u * kGemmThreads, n_pad * 8, Bg, p.b.ld, n_pad, n_here, n0);
+    for (int u = 0; u < ITEMS_B; u++) ib[u] = make_item<B_K>(tid + u * kGemmThreads, n_pad * 8, p.b.ld, n_pad, n_here, n0);
 
     if (issuer) {
         // ---- the MMA warp: waits for a stage to be full, issues its 3 x 4 (x halves) products, commits them to the
@@ -314,20 +333,30 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
             mbar_wait(smem_u32(&bars[s]), (it / kStages) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                if (p.debug != 1) {
+                if ((p.debug & 3) != 1) {
                     const uint32_t st = smem_base + s * stage_bytes;
                     const uint32_t b_hi = st, b_lo = st + b_bytes;
                     const uint32_t a_hi = tmem_base + kAColBase + 64 * s, a_lo = a_hi + 32;
+                    // EXPERIMENT (profiling knob >> 2): how the 288 accumulator columns are cut into instructions
+                    int seg_n[3] = {n_mma, n_mma, 0}, nseg = halves;
+                    const int mode = p.debug >> 2;
+                    if (mode == 1) { seg_n[0] = 256; seg_n[1] = n_pad - 256; nseg = 2; }
+                    if (mode == 2) { seg_n[0] = 96; seg_n[1] = 96; seg_n[2] = n_pad - 192; nseg = 3; }
+                    if (mode == 3) { seg_n[0] = 192; seg_n[1] = n_pad - 192; nseg = 2; }
+                    if (mode == 4) { seg_n[0] = 128; seg_n[1] = 128; seg_n[2] = n_pad - 256; nseg = 3; }
 #pragma unroll
                     for (int ks = 0; ks < kChunkK / 8; ks++) {
-                        for (int h = 0; h < halves; h++) {
-                            const uint32_t boff = 32 * ks + h * n_mma * 128;      // n_mma % 8 == 0: whole swizzle atoms
-                            const uint32_t d = tmem_base + h * n_mma;
+                        int n_at = 0;
+                        for (int h = 0; h < nseg; h++) {
+                            const uint32_t boff = 32 * ks + n_at * 128;      // n_mma % 8 == 0: whole swizzle atoms
+                            const uint32_t d = tmem_base + n_at;
+                            const uint32_t idesc_h = umma_idesc_tf32(kTileM, seg_n[h]);
+                            n_at += seg_n[h];
                             const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
                             // small terms first: a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
-                            umma_tf32_ts(d, a_lo + 8 * ks, umma_desc(b_hi + boff), idesc, first);
-                            umma_tf32_ts(d, a_hi + 8 * ks, umma_desc(b_lo + boff), idesc, 1u);
-                            umma_tf32_ts(d, a_hi + 8 * ks, umma_desc(b_hi + boff), idesc, 1u);
+                            umma_tf32_ts(d, a_lo + 8 * ks, umma_desc(b_hi + boff), idesc_h, first);
+                            umma_tf32_ts(d, a_hi + 8 * ks, umma_desc(b_lo + boff), idesc_h, 1u);
+                            umma_tf32_ts(d, a_hi + 8 * ks, umma_desc(b_hi + boff), idesc_h, 1u);
                         }
                     }
                 }
@@ -336,111 +365,161 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
             }
             __syncwarp();
         }
-    } else
-    for (int c = c_begin; c < c_end; c++) {
-        const int it = c - c_begin, s = it % kStages;
-        const int k0 = c * kChunkK;
-        const int k_left = p.K - k0;
-        const long long adv_a = A_K ? (long long)k0 : (long long)k0 * p.a.ld;
-        const long long adv_b = B_K ? (long long)k0 : (long long)k0 * p.b.ld;
-        // ---- global loads of this chunk (issued before waiting for the stage: latency overlaps the running MMAs)
-        float xa[8], ya[8];
-        float4 vb[ITEMS_B];
-        if (p.debug != 2) {
+    } else {
+        // ---- producers.  A: the loads of chunk c+1 are issued before chunk c is transformed / split / stored (two register
+        //      sets), so a thread always has a chunk of global loads in flight.  B: staged through registers, or -- packed
+        //      operand (weights pre-split and pre-swizzled by hrl_board_pack) -- ONE bulk copy per stage issued by thread 0.
+        float xa[8], ya[8], xn[8], yn[8];
+        auto load_a = [&](int c, float *x, float *y) {
+            const int k0 = c * kChunkK, k_left = p.K - k0;
+            const long long adv_a = A_K ? (long long)k0 : (long long)k0 * p.a.ld;
 #pragma unroll
-            for (int e = 0; e < 8; e++) xa[e] = ya[e] = 0.f;
-            if (a_live) {
-                const float *q = a_ptr + adv_a;
-                if (A_K && vec_a && a_k + 7 < k_left) {
-                    const float4 u0 = __ldg(reinterpret_cast<const float4 *>(q)), u1 = __ldg(reinterpret_cast<const float4 *>(q) + 1);
-                    xa[0] = u0.x; xa[1] = u0.y; xa[2] = u0.z; xa[3] = u0.w; xa[4] = u1.x; xa[5] = u1.y; xa[6] = u1.z; xa[7] = u1.w;
-                    if (p.a.ptr2) {
-                        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(q + a2)), w1 = __ldg(reinterpret_cast<const float4 *>(q + a2) + 1);
-                        ya[0] = w0.x; ya[1] = w0.y; ya[2] = w0.z; ya[3] = w0.w; ya[4] = w1.x; ya[5] = w1.y; ya[6] = w1.z; ya[7] = w1.w;
-                    }
-                } else {
-                    const long long st = A_K ? 1 : p.a.ld;
-#pragma unroll
-                    for (int e = 0; e < 8; e++)
-                        if (a_k + e < k_left) {
-                            xa[e] = __ldg(q + e * st);
-                            if (p.a.ptr2) ya[e] = __ldg(q + a2 + e * st);
-                        }
+            for (int e = 0; e < 8; e++) x[e] = y[e] = 0.f;
+            if (!a_live || (p.debug & 3) == 2) return;
+            const float *q = a_ptr + adv_a;
+            if (A_K && vec_a && a_k + 7 < k_left) {
+                const float4 u0 = __ldg(reinterpret_cast<const float4 *>(q)), u1 = __ldg(reinterpret_cast<const float4 *>(q) + 1);
+                x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w; x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
+                if (p.a.ptr2) {
+                    const float4 w0 = __ldg(reinterpret_cast<const float4 *>(q + a2)), w1 = __ldg(reinterpret_cast<const float4 *>(q + a2) + 1);
+                    y[0] = w0.x; y[1] = w0.y; y[2] = w0.z; y[3] = w0.w; y[4] = w1.x; y[5] = w1.y; y[6] = w1.z; y[7] = w1.w;
                 }
-                if (p.a.p != nullptr) {
-                    float pp[8], qq[8], rr[8];
-                    if (p.a.feature_is_row) {
+            } else {
+                const long long st = A_K ? 1 : p.a.ld;
 #pragma unroll
-                        for (int e = 0; e < 8; e++) { pp[e] = a_pr; qq[e] = a_qr; rr[e] = a_rr; }
-                    } else if (a_k + 7 < k_left) {      // constants of this warp's 8 reduction indices: uniform over the warp, vector loads
-                        const int f = k0 + a_k;
-                        const float4 p0 = __ldg(reinterpret_cast<const float4 *>(p.a.p + f)), p1 = __ldg(reinterpret_cast<const float4 *>(p.a.p + f) + 1);
-                        const float4 r0 = __ldg(reinterpret_cast<const float4 *>(p.a.r + f)), r1 = __ldg(reinterpret_cast<const float4 *>(p.a.r + f) + 1);
-                        pp[0] = p0.x; pp[1] = p0.y; pp[2] = p0.z; pp[3] = p0.w; pp[4] = p1.x; pp[5] = p1.y; pp[6] = p1.z; pp[7] = p1.w;
-                        rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
-                        if (p.a.q) {
-                            const float4 q0 = __ldg(reinterpret_cast<const float4 *>(p.a.q + f)), q1 = __ldg(reinterpret_cast<const float4 *>(p.a.q + f) + 1);
-                            qq[0] = q0.x; qq[1] = q0.y; qq[2] = q0.z; qq[3] = q0.w; qq[4] = q1.x; qq[5] = q1.y; qq[6] = q1.z; qq[7] = q1.w;
-                        } else {
+                for (int e = 0; e < 8; e++)
+                    if (a_k + e < k_left) {
+                        x[e] = __ldg(q + e * st);
+                        if (p.a.ptr2) y[e] = __ldg(q + a2 + e * st);
+                    }
+            }
+        };
+        if (PACKED && c_begin < c_end) load_a(c_begin, xa, ya);
+        for (int c = c_begin; c < c_end; c++) {
+            const int it = c - c_begin, s = it % kStages;
+            const int k0 = c * kChunkK;
+            const int k_left = p.K - k0;
+            const long long adv_b = B_K ? (long long)k0 : (long long)k0 * p.b.ld;
+            float4 vb[ITEMS_B];
+            if (PACKED) {
+                if (c + 1 < c_end) load_a(c + 1, xn, yn);        // next chunk's A in flight while this one is processed
+            } else {
+                load_a(c, xa, ya);                               // (B staged through registers: no room for a second A set)
+            }
+            if ((p.debug & 3) != 2 && !PACKED) {
+                // all the loads first (one exposed latency per chunk, not one per item), then the transforms
 #pragma unroll
-                            for (int e = 0; e < 8; e++) qq[e] = 0.f;
+                for (int u = 0; u < ITEMS_B; u++) vb[u] = load_item<B_K>(ib[u], Bg, p.b.ld, vec_b, adv_b, k_left);
+                if (b_rows) {
+#pragma unroll
+                    for (int u = 0; u < ITEMS_B; u++) {
+                        if (!ib[u].live()) continue;
+                        const float pc = b_consts[0][ib[u].row() - n0], rc = b_consts[1][ib[u].row() - n0];
+                        float4 v;
+                        v.x = fmaf(vb[u].x, pc, rc); v.y = fmaf(vb[u].y, pc, rc); v.z = fmaf(vb[u].z, pc, rc); v.w = fmaf(vb[u].w, pc, rc);
+                        if (p.b.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (k_left < kChunkK) {                  // the reduction tail stays exactly zero
+                            const int k = ib[u].k();
+                            if (k + 0 >= k_left) v.x = 0.f;
+                            if (k + 1 >= k_left) v.y = 0.f;
+                            if (k + 2 >= k_left) v.z = 0.f;
+                            if (k + 3 >= k_left) v.w = 0.f;
                         }
+                        vb[u] = v;
+                    }
+                } else if (p.b.p != nullptr) {
+#pragma unroll
+                    for (int u = 0; u < ITEMS_B; u++) {
+                        const float4 y = p.b.ptr2 ? load_item<B_K>(ib[u], Bg, p.b.ld, vec_b, adv_b + b2, k_left) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        vb[u] = transform_item(p.b, ib[u], vb[u], y, k0, k_left);
+                    }
+                }
+            }
+            // operand transform of the current A slice
+            if (p.a.p != nullptr && a_live && (p.debug & 3) != 2) {
+                float pp[8], qq[8], rr[8];
+                if (p.a.feature_is_row) {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { pp[e] = a_pr; qq[e] = a_qr; rr[e] = a_rr; }
+                } else if (a_k + 7 < k_left) {      // constants of this warp's 8 reduction indices: uniform over the warp, vector loads
+                    const int f = k0 + a_k;
+                    const float4 p0 = __ldg(reinterpret_cast<const float4 *>(p.a.p + f)), p1 = __ldg(reinterpret_cast<const float4 *>(p.a.p + f) + 1);
+                    const float4 r0 = __ldg(reinterpret_cast<const float4 *>(p.a.r + f)), r1 = __ldg(reinterpret_cast<const float4 *>(p.a.r + f) + 1);
+                    pp[0] = p0.x; pp[1] = p0.y; pp[2] = p0.z; pp[3] = p0.w; pp[4] = p1.x; pp[5] = p1.y; pp[6] = p1.z; pp[7] = p1.w;
+                    rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+                    if (p.a.q) {
+                        const float4 q0 = __ldg(reinterpret_cast<const float4 *>(p.a.q + f)), q1 = __ldg(reinterpret_cast<const float4 *>(p.a.q + f) + 1);
+                        qq[0] = q0.x; qq[1] = q0.y; qq[2] = q0.z; qq[3] = q0.w; qq[4] = q1.x; qq[5] = q1.y; qq[6] = q1.z; qq[7] = q1.w;
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 8; e++) {
-                            const bool in = a_k + e < k_left;
-                            pp[e] = in ? __ldg(p.a.p + k0 + a_k + e) : 0.f;
-                            rr[e] = in ? __ldg(p.a.r + k0 + a_k + e) : 0.f;
-                            qq[e] = (in && p.a.q) ? __ldg(p.a.q + k0 + a_k + e) : 0.f;
-                        }
+                        for (int e = 0; e < 8; e++) qq[e] = 0.f;
                     }
+                } else {
 #pragma unroll
                     for (int e = 0; e < 8; e++) {
-                        if (a_k + e < k_left) {
-                            const float v = fmaf(xa[e], pp[e], fmaf(ya[e], qq[e], rr[e]));
-                            xa[e] = p.a.relu ? fmaxf(v, 0.f) : v;
-                        }
+                        const bool in = a_k + e < k_left;
+                        pp[e] = in ? __ldg(p.a.p + k0 + a_k + e) : 0.f;
+                        rr[e] = in ? __ldg(p.a.r + k0 + a_k + e) : 0.f;
+                        qq[e] = (in && p.a.q) ? __ldg(p.a.q + k0 + a_k + e) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    if (a_k + e < k_left) {
+                        const float v = fmaf(xa[e], pp[e], fmaf(ya[e], qq[e], rr[e]));
+                        xa[e] = p.a.relu ? fmaxf(v, 0.f) : v;
                     }
                 }
             }
+            if (it >= kStages) mbar_wait(smem_u32(&bars[kStages + s]), ((it / kStages) - 1) & 1);      // the MMAs that read this stage are done
+            if (PACKED && tid == 0) {           // weights: one bulk copy of the stage's pre-split, pre-swizzled image
+                const uint32_t bar = smem_u32(&bars[s]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(stage_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_base + s * stage_bytes),
+                             "l"(reinterpret_cast<const uint8_t *>(p.b.ptr) + (size_t)c * stage_bytes), "r"(stage_bytes), "r"(bar)
+                             : "memory");
+            }
+            if ((p.debug & 3) != 2) {
+                float hi[8], lo[8];
 #pragma unroll
-            for (int u = 0; u < ITEMS_B; u++) {
-                vb[u] = load_item<B_K>(ib[u], p.b.ld, vec_b, adv_b, k_left);
-                if (p.b.p != nullptr) {
-                    const float4 y = p.b.ptr2 ? load_item<B_K>(ib[u], p.b.ld, vec_b, adv_b + b2, k_left) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    vb[u] = transform_item(p.b, ib[u], vb[u], y, k0, k_left);
+                for (int e = 0; e < 8; e++) {
+                    hi[e] = __uint_as_float(__float_as_uint(xa[e]) & 0xFFFFE000u);
+                    lo[e] = xa[e] - hi[e];
                 }
+                tmem_st8(a_taddr + 64 * s, hi);
+                tmem_st8(a_taddr + 64 * s + 32, lo);
+                if (!PACKED) {
+                    uint8_t *stp = smem + s * stage_bytes;
+#pragma unroll
+                    for (int u = 0; u < ITEMS_B; u++) {
+                        if (ib[u].slot != 0xFFFFFFFFu) {
+                            float4 h4, l4;
+                            split_tf32(vb[u], h4, l4);
+                            *reinterpret_cast<float4 *>(stp + ib[u].slot) = h4;
+                            *reinterpret_cast<float4 *>(stp + b_bytes + ib[u].slot) = l4;
+                        }
+                    }
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[s])) : "memory");      // this stage is full
+            if (PACKED) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) { xa[e] = xn[e]; ya[e] = yn[e]; }
             }
         }
-        if (it >= kStages) mbar_wait(smem_u32(&bars[kStages + s]), ((it / kStages) - 1) & 1);      // the MMAs that read this stage are done
-        if (p.debug != 2) {
-            float hi[8], lo[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                hi[e] = __uint_as_float(__float_as_uint(xa[e]) & 0xFFFFE000u);
-                lo[e] = xa[e] - hi[e];
-            }
-            tmem_st8(a_taddr + 64 * s, hi);
-            tmem_st8(a_taddr + 64 * s + 32, lo);
-            uint8_t *stp = smem + s * stage_bytes;
-#pragma unroll
-            for (int u = 0; u < ITEMS_B; u++) {
-                if (ib[u].slot != 0xFFFFFFFFu) {
-                    float4 h4, l4;
-                    split_tf32(vb[u], h4, l4);
-                    *reinterpret_cast<float4 *>(stp + ib[u].slot) = h4;
-                    *reinterpret_cast<float4 *>(stp + b_bytes + ib[u].slot) = l4;
-                }
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[s])) : "memory");      // this stage is full
     }
 
     // ---- epilogue: TMEM -> registers -> shared-memory tile (padded rows) -> coalesced global stores.
     // (a thread holds ONE row of the accumulator: storing from registers would touch 32 cache lines per warp instruction)
+    //   HRL_GEMM_EP_RELU        C = max(acc, 0)
+    //   HRL_GEMM_EP_STATS       C = acc, plus per-column sum and sum of squares over the tile's rows
+    //   HRL_GEMM_EP_MASK_STATS  C = acc * (z > 0) with z = y*scale+shift of the pre-activation tile y (the ReLU
+    //                           backward), plus per-column sums of C and of C * xhat, xhat = (y - mean) * rstd
+    //                           (the two batch sums the BatchNorm backward needs)
     const int n_chunks_here = c_end - c_begin;
     float *Cg = p.C + (long long)split * p.c_split_stride;
     const int q = warp & 3, group = warp >> 2;
@@ -448,132 +527,145 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
     const int cols_per_group = ((n_pad + kGroups - 1) / kGroups + 7) / 8 * 8;
     const int ldt = n_pad + 4;                           // row stride = 16 (mod 128) bytes: conflict-free 16-byte stores
     float *tile = reinterpret_cast<float *>(smem);       // the stages are free once the last MMAs have completed
+    const int ep = p.epilogue;
+    // copy-out mapping: a thread owns ONE group of 4 columns (its constants and column sums live in 16 registers) and the
+    // rows my_r, my_r + rpp, ...; consecutive threads = consecutive 16 bytes of a row, then of the next row
+    const bool vec_c = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cg) & 15) == 0) && (n0 % 4 == 0) && (n_here % 4 == 0);
+    const int cols4 = n_here >> 2;
+    // rows per pass; capped by the column-sum scratch the host sized for the widest tile (a narrower last tile would take more)
+    const int rpp = vec_c ? min(kGemmThreads / cols4, kGemmThreads / max(1, (n_pad - 12) / 4)) : 1;
+    const int my_r = vec_c ? tid / cols4 : 0, my_c4 = tid - my_r * cols4;
+    const bool mine = vec_c && !issuer && my_r < rpp;
+    const bool masked = ep == HRL_GEMM_EP_MASK_STATS;
+    const bool vec_y = masked && (p.ep_ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.ep_y) & 15) == 0);
+    constexpr int kAhead = 4;                              // rows of the pre-activation tile in flight per thread
+    float4 yq[kAhead];
+    auto load_y = [&](int r) -> float4 {
+        const float *yp = p.ep_y + (long long)(m0 + r) * p.ep_ldy + n0 + 4 * my_c4;
+        if (vec_y) return __ldg(reinterpret_cast<const float4 *>(yp));
+        return make_float4(__ldg(yp), __ldg(yp + 1), __ldg(yp + 2), __ldg(yp + 3));
+    };
+    if (masked && mine) {            // issued before the wait for the last MMAs: in flight while the accumulator drains
+#pragma unroll
+        for (int u = 0; u < kAhead; u++) {
+            const int r = my_r + u * rpp;
+            yq[u] = r < rows_a ? load_y(r) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     if (n_chunks_here > 0) {
         mbar_wait(smem_u32(&bars[2 * kStages]), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     if (!issuer) {
         float *trow = tile + (q * 32 + (tid & 31)) * ldt;
-        for (int cb = 0; cb < cols_per_group; cb += 8) {
-            const int col = group * cols_per_group + cb;
-            if (col >= n_pad) break;
-            uint32_t r[8];
-            if (n_chunks_here > 0) {
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                             : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
+        const uint32_t trow_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        auto put = [&](int col, const uint32_t *r, int n) {
 #pragma unroll
-                for (int e = 0; e < 8; e++) r[e] = 0u;
-            }
-            float v[8];
+            for (int e = 0; e < 32; e += 4) {
+                if (e >= n) break;
+                float v[4];
 #pragma unroll
-            for (int e = 0; e < 8; e++) {
-                v[e] = __uint_as_float(r[e]);
-                if (p.bias != nullptr && col + e < n_here) v[e] += __ldg(p.bias + n0 + col + e);
+                for (int i = 0; i < 4; i++) {
+                    v[i] = n_chunks_here > 0 ? __uint_as_float(r[e + i]) : 0.f;
+                    if (p.bias != nullptr && col + e + i < n_here) v[i] += __ldg(p.bias + n0 + col + e + i);
+                }
+                *reinterpret_cast<float4 *>(trow + col + e) = make_float4(v[0], v[1], v[2], v[3]);
             }
-            reinterpret_cast<float4 *>(trow + col)[0] = make_float4(v[0], v[1], v[2], v[3]);
-            reinterpret_cast<float4 *>(trow + col)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        };
+        const int col_end = min(n_pad, (group + 1) * cols_per_group);
+        int col = group * cols_per_group;
+        for (; col + 32 <= col_end; col += 32) {            // 32 columns per tensor-memory load (one wait per 128 bytes of a row)
+            uint32_t r[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+                "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(trow_addr + (uint32_t)col));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            put(col, r, 32);
+        }
+        for (; col < col_end; col += 8) {
+            uint32_t r[32];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                         : "r"(trow_addr + (uint32_t)col));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            put(col, r, 8);
         }
     }
     __syncthreads();
     {
-        // copy-out: a warp owns rows warp, warp+16, ...; a lane owns the float4 column groups lane, lane+32, lane+64.
-        // (the MMA warp has nothing to do here but takes part in the barriers)
-        //   HRL_GEMM_EP_RELU        C = max(acc, 0)
-        //   HRL_GEMM_EP_STATS       C = acc, plus per-column sum and sum of squares over the tile's rows
-        //   HRL_GEMM_EP_MASK_STATS  C = acc * (z > 0) with z = y*scale+shift of the pre-activation tile y (the ReLU
-        //                           backward), plus per-column sums of C and of C * xhat, xhat = (y - mean) * rstd
-        //                           (the two batch sums the BatchNorm backward needs)
-        const bool vec_c = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cg) & 15) == 0) && (n0 % 4 == 0) && (n_here % 4 == 0);
-        const int ep = p.epilogue;
-        const bool stats = (ep == HRL_GEMM_EP_STATS || ep == HRL_GEMM_EP_MASK_STATS) && p.col_partials != nullptr;
-        constexpr int kGroupsPerLane = (kMaxN / 4 + 31) / 32;      // 3
-        float s1[kGroupsPerLane][4], s2[kGroupsPerLane][4];
+        const bool stats = (ep == HRL_GEMM_EP_STATS || masked) && p.col_partials != nullptr;
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        if (mine) {
+            float k_sc[4] = {1.f, 1.f, 1.f, 1.f}, k_sh[4] = {0.f, 0.f, 0.f, 0.f}, k_mu[4] = {0.f, 0.f, 0.f, 0.f}, k_rs[4] = {1.f, 1.f, 1.f, 1.f};
+            if (masked) {
 #pragma unroll
-        for (int g = 0; g < kGroupsPerLane; g++)
-#pragma unroll
-            for (int e = 0; e < 4; e++) s1[g][e] = s2[g][e] = 0.f;
-        if (issuer) {
-        } else if (vec_c) {
-            const bool vec_y = ep == HRL_GEMM_EP_MASK_STATS && (p.ep_ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.ep_y) & 15) == 0);
-            // a lane always handles the same columns: their constants are loaded once, not per row
-            float k_sc[kGroupsPerLane][4], k_sh[kGroupsPerLane][4], k_mu[kGroupsPerLane][4], k_rs[kGroupsPerLane][4];
-            if (ep == HRL_GEMM_EP_MASK_STATS) {
-#pragma unroll
-                for (int g = 0; g < kGroupsPerLane; g++)
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int col = n0 + 4 * (lane + 32 * g) + e;
-                        const bool in = 4 * (lane + 32 * g) + e < n_here;
-                        k_sc[g][e] = (in && p.ep_scale) ? __ldg(p.ep_scale + col) : 1.f;
-                        k_sh[g][e] = (in && p.ep_shift) ? __ldg(p.ep_shift + col) : 0.f;
-                        k_mu[g][e] = (in && p.ep_mean) ? __ldg(p.ep_mean + col) : 0.f;
-                        k_rs[g][e] = (in && p.ep_rstd) ? __ldg(p.ep_rstd + col) : 1.f;
-                    }
+                for (int e = 0; e < 4; e++) {
+                    const int col = n0 + 4 * my_c4 + e;
+                    if (p.ep_scale) k_sc[e] = __ldg(p.ep_scale + col);
+                    if (p.ep_shift) k_sh[e] = __ldg(p.ep_shift + col);
+                    if (p.ep_mean) k_mu[e] = __ldg(p.ep_mean + col);
+                    if (p.ep_rstd) k_rs[e] = __ldg(p.ep_rstd + col);
+                }
             }
-            for (int r = warp; r < rows_a; r += kGemmThreads / 32) {
-                const float *src = tile + r * ldt;
-                float *dst = Cg + (long long)(m0 + r) * p.ldc + n0;
+            for (int r0 = my_r; r0 < rows_a; r0 += kAhead * rpp) {
 #pragma unroll
-                for (int g = 0; g < kGroupsPerLane; g++) {
-                    const int c4 = lane + 32 * g;
-                    if (c4 >= n_here / 4) break;
-                    float4 v = reinterpret_cast<const float4 *>(src)[c4];
+                for (int u = 0; u < kAhead; u++) {
+                    const int r = r0 + u * rpp;
+                    if (r >= rows_a) break;
+                    float4 v = reinterpret_cast<const float4 *>(tile + r * ldt)[my_c4];
                     if (ep == HRL_GEMM_EP_RELU) {
                         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                     } else if (ep == HRL_GEMM_EP_STATS) {
-                        s1[g][0] += v.x; s1[g][1] += v.y; s1[g][2] += v.z; s1[g][3] += v.w;
-                        s2[g][0] = fmaf(v.x, v.x, s2[g][0]); s2[g][1] = fmaf(v.y, v.y, s2[g][1]);
-                        s2[g][2] = fmaf(v.z, v.z, s2[g][2]); s2[g][3] = fmaf(v.w, v.w, s2[g][3]);
-                    } else if (ep == HRL_GEMM_EP_MASK_STATS) {
-                        const int col = n0 + 4 * c4;
-                        const float *yp = p.ep_y + (long long)(m0 + r) * p.ep_ldy + col;
-                        float4 y;
-                        if (vec_y) y = __ldg(reinterpret_cast<const float4 *>(yp));
-                        else y = make_float4(__ldg(yp), __ldg(yp + 1), __ldg(yp + 2), __ldg(yp + 3));
-                        float yv[4] = {y.x, y.y, y.z, y.w}, vv[4] = {v.x, v.y, v.z, v.w};
+                        s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+                        s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]);
+                        s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
+                    } else if (masked) {
+                        const float4 y = yq[u];
+                        const int rn = r + kAhead * rpp;
+                        if (rn < rows_a) yq[u] = load_y(rn);              // the row this slot serves next
+                        const float yv[4] = {y.x, y.y, y.z, y.w};
+                        float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
-                            const float z = fmaf(yv[e], k_sc[g][e], k_sh[g][e]);
+                            const float z = fmaf(yv[e], k_sc[e], k_sh[e]);
                             const float d = z > 0.f ? vv[e] : 0.f;
-                            const float xh = (yv[e] - k_mu[g][e]) * k_rs[g][e];
+                            const float xh = (yv[e] - k_mu[e]) * k_rs[e];
                             vv[e] = d;
-                            s1[g][e] += d;
-                            s2[g][e] = fmaf(d, xh, s2[g][e]);
+                            s1[e] += d;
+                            s2[e] = fmaf(d, xh, s2[e]);
                         }
                         v = make_float4(vv[0], vv[1], vv[2], vv[3]);
                     }
-                    reinterpret_cast<float4 *>(dst)[c4] = v;
+                    reinterpret_cast<float4 *>(Cg + (long long)(m0 + r) * p.ldc + n0)[my_c4] = v;
                 }
             }
-        } else {
+        } else if (!vec_c && !issuer) {
             for (int r = warp; r < rows_a; r += kGemmThreads / 32) {
                 const float *src = tile + r * ldt;
                 float *dst = Cg + (long long)(m0 + r) * p.ldc + n0;
                 for (int c1 = lane; c1 < n_here; c1 += 32) dst[c1] = (ep == HRL_GEMM_EP_RELU) ? fmaxf(src[c1], 0.f) : src[c1];
             }
         }
-        if (stats) {
-            // per-warp column sums -> shared memory (behind the tile) -> fixed-order sum over the 16 warps -> global partials
-            float *red = tile + kTileM * ldt;                 // [16 warps][2][n_pad]
+        if (stats) {       // (the statistics epilogues require vec_c: checked by the host)
+            // per-thread column sums -> shared memory (behind the tile) -> fixed-order sum over the row passes -> global partials
+            float *red = tile + kTileM * ldt;                 // [rpp][2][n_pad]
+            if (mine) {
 #pragma unroll
-            for (int g = 0; g < kGroupsPerLane; g++) {
-                const int c4 = lane + 32 * g;
-                if (c4 < n_pad / 4 && !issuer) {
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        red[(warp * 2 + 0) * n_pad + 4 * c4 + e] = s1[g][e];
-                        red[(warp * 2 + 1) * n_pad + 4 * c4 + e] = s2[g][e];
-                    }
+                for (int e = 0; e < 4; e++) {
+                    red[(my_r * 2 + 0) * n_pad + 4 * my_c4 + e] = s1[e];
+                    red[(my_r * 2 + 1) * n_pad + 4 * my_c4 + e] = s2[e];
                 }
             }
             __syncthreads();
             for (int i = tid; i < 2 * n_here && !issuer; i += kGemmThreads) {
                 const int which = i / n_here, col = i - which * n_here;
                 float acc = 0.f;
-                for (int w = 0; w < kGemmThreads / 32; w++) acc += red[(w * 2 + which) * n_pad + col];
+                for (int w = 0; w < rpp; w++) acc += red[(w * 2 + which) * n_pad + col];
                 p.col_partials[((long long)blockIdx.x * 2 + which) * p.N + n0 + col] = acc;
             }
         }
@@ -619,10 +711,12 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
     const int64_t M = g.M, N = g.N, K = g.K;
     int splits = g.splits;
     HRL_REQUIRE(g.a.ptr && g.b.ptr && (g.C || (splits > 1 && g.workspace)), HRL_ERR_BAD_ARG, "hrl_gemm_fused: NULL pointer");
-    HRL_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), HRL_ERR_BAD_ARG,
+    HRL_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 22) && K < (1ll << 31) && g.b.ld < (1ll << 22), HRL_ERR_BAD_ARG,
                 "hrl_gemm_fused: bad dimensions (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
-    HRL_REQUIRE(g.a.ld >= (g.a.kmajor ? K : M) && g.b.ld >= (g.b.kmajor ? K : N) && (g.C == nullptr || g.ldc >= N), HRL_ERR_BAD_ARG,
-                "hrl_gemm_fused: leading dimension smaller than the row length");
+    HRL_REQUIRE(g.a.ld >= (g.a.kmajor ? K : M) && (g.b.packed || g.b.ld >= (g.b.kmajor ? K : N)) && (g.C == nullptr || g.ldc >= N),
+                HRL_ERR_BAD_ARG, "hrl_gemm_fused: leading dimension smaller than the row length");
+    HRL_REQUIRE(!g.a.packed && (!g.b.packed || (N <= hrl::kMaxN && g.b.p == nullptr && (reinterpret_cast<uintptr_t>(g.b.ptr) & 15) == 0)),
+                HRL_ERR_BAD_ARG, "hrl_gemm_fused: only an untransformed B operand of at most 288 rows can be a packed image");
     HRL_REQUIRE((g.a.p == nullptr) == (g.a.r == nullptr) && (g.b.p == nullptr) == (g.b.r == nullptr) &&
                     (g.a.ptr2 == nullptr || (g.a.p && g.a.q)) && (g.b.ptr2 == nullptr || (g.b.p && g.b.q)),
                 HRL_ERR_BAD_ARG, "hrl_gemm_fused: an operand transform needs p and r (and q with a second source)");
@@ -645,7 +739,7 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
     auto operand = [](const HrlGemmOperand &o) {
         GemmOperand r;
         r.ptr = o.ptr; r.ptr2 = o.ptr2; r.p = o.p; r.q = o.q; r.r = o.r; r.ld = o.ld;
-        r.kmajor = o.kmajor ? 1 : 0; r.relu = o.relu ? 1 : 0; r.feature_is_row = o.feature_is_row ? 1 : 0;
+        r.kmajor = o.kmajor ? 1 : 0; r.relu = o.relu ? 1 : 0; r.feature_is_row = o.feature_is_row ? 1 : 0; r.packed = o.packed ? 1 : 0;
         return r;
     };
     p.a = operand(g.a);
@@ -665,17 +759,19 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
         p.C = g.C; p.ldc = g.ldc; p.c_split_stride = 0;
     }
     size_t smem_bytes = 1024 + (size_t)kStages * (2 * (size_t)n_pad * kChunkK * 4);
-    const size_t ep_bytes = 1024 + ((size_t)kTileM * (n_pad + 4) + 32 * (size_t)n_pad) * 4;      // epilogue tile + column-sum scratch
+    const size_t red_rows = (size_t)kGemmThreads / (size_t)((n_pad - 12) / 4 > 0 ? (n_pad - 12) / 4 : 1);      // copy-out row passes (as the kernel)
+    const size_t ep_bytes = 1024 + ((size_t)kTileM * (n_pad + 4) + 2 * red_rows * (size_t)n_pad) * 4;      // epilogue tile + column-sum scratch
     if (smem_bytes < ep_bytes) smem_bytes = ep_bytes;
     const dim3 grid((unsigned)((M + kTileM - 1) / kTileM), (unsigned)n_tiles, (unsigned)splits);
     const int items_b = (n_pad * 8 + kGemmThreads - 1) / kGemmThreads;
     constexpr int IA = kTileM * 8 / kGemmThreads;
-#define HRL_GEMM_LAUNCH2(AK, BK, IB)                                                                                       \
+#define HRL_GEMM_LAUNCH3(AK, BK, IB, PK)                                                                                   \
     {                                                                                                                     \
-        HRL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<AK, BK, IA, IB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        HRL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<AK, BK, IA, IB, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                             (int)smem_bytes));                                                            \
-        gemm_tf32x3_kernel<AK, BK, IA, IB><<<grid, kGemmBlock, smem_bytes, stream>>>(p, n_pad);                          \
+        gemm_tf32x3_kernel<AK, BK, IA, IB, PK><<<grid, kGemmBlock, smem_bytes, stream>>>(p, n_pad);                      \
     }
+#define HRL_GEMM_LAUNCH2(AK, BK, IB) HRL_GEMM_LAUNCH3(AK, BK, IB, false)
 #define HRL_GEMM_LAUNCH(IB)                                                                    \
     {                                                                                         \
         if (p.a.kmajor && p.b.kmajor) HRL_GEMM_LAUNCH2(true, true, IB)                        \
@@ -683,11 +779,15 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
         else if (p.b.kmajor) HRL_GEMM_LAUNCH2(false, true, IB)                                \
         else HRL_GEMM_LAUNCH2(false, false, IB)                                               \
     }
-    if (items_b <= 1) HRL_GEMM_LAUNCH(1)
+    if (p.b.packed) {
+        if (p.a.kmajor) HRL_GEMM_LAUNCH3(true, true, 1, true)
+        else HRL_GEMM_LAUNCH3(false, true, 1, true)
+    } else if (items_b <= 1) HRL_GEMM_LAUNCH(1)
     else if (items_b <= 3) HRL_GEMM_LAUNCH(3)
     else HRL_GEMM_LAUNCH(5)
 #undef HRL_GEMM_LAUNCH
 #undef HRL_GEMM_LAUNCH2
+#undef HRL_GEMM_LAUNCH3
     HRL_CUDA_CHECK(cudaGetLastError());
     if (splits > 1 && g.C != nullptr) {       // C == NULL: the caller consumes the slice partials itself (hrl_board_fold)
         const long long n = (long long)M * N;

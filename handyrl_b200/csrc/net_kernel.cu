@@ -29,6 +29,31 @@ __global__ void board_expand_kernel(const float *__restrict__ w, float *__restri
     }
 }
 
+// dense element (row = (o,q), col = (i,p)) of the convolution, straight into packed B-operand images of the tcgen05 GEMM
+// (csrc/gemm_kernel.cu): image[chunk = k / 32][hi | lo][row][slot (k % 32) / 4 ^ (row & 7)][k % 4]
+__device__ __forceinline__ void pack_store(float *image, int n_pad, int row, int k, float v) {
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const long long chunk = k >> 5;
+    const int j = (k & 31) >> 2, e = k & 3;
+    float *base = image + chunk * (2ll * n_pad * 32) + (long long)row * 32 + (((j ^ (row & 7)) << 2) + e);
+    base[0] = hi;
+    base[(long long)n_pad * 32] = v - hi;
+}
+
+__global__ void board_pack_kernel(const float *__restrict__ w, int Cout, int Cin, int kh, int kw, int H, int W, float *__restrict__ image_fwd,
+                                  int fwd_pad, int fwd_row0, float *__restrict__ image_bwd, int bwd_pad, int bwd_k0) {
+    const int HW = H * W;
+    const long long n = (long long)Cout * HW * Cin * HW;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(idx % (Cin * HW)), row = (int)(idx / (Cin * HW));
+        const int o = row / HW, q = row - o * HW, i = col / HW, p = col - i * HW;
+        const int a = p / W - q / W + kh / 2, b = p % W - q % W + kw / 2;
+        const float v = (a >= 0 && a < kh && b >= 0 && b < kw) ? __ldg(w + ((long long)(o * Cin + i) * kh + a) * kw + b) : 0.f;
+        if (image_fwd) pack_store(image_fwd, fwd_pad, fwd_row0 + row, col, v);       // rows = output features, reduction = input features
+        if (image_bwd) pack_store(image_bwd, bwd_pad, col, bwd_k0 + row, v);          // rows = input features, reduction = output features
+    }
+}
+
 // one CTA per output channel o: its HW rows of the dense gradient (a contiguous slab of HW * Cin*HW floats per K slice) are
 // summed over the slices with coalesced reads (fixed order -> deterministic) into shared memory, then folded onto the taps
 __global__ void board_fold_kernel(const float *__restrict__ ddense, int splits, long long split_stride, float *__restrict__ dw, int Cout,
@@ -197,6 +222,31 @@ extern "C" int hrl_board_expand(const float *w, float *dense, int32_t Cout, int3
                 "hrl_board_expand: NULL pointer or bad shape (odd kernels only)");
     const long long n = (long long)Cout * Cin * H * W * H * W;
     board_expand_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, dense, Cout, Cin, kh, kw, H, W);
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
+
+extern "C" int32_t hrl_gemm_padded_rows(int64_t N) {
+    int n = (int)((N + 15) / 16 * 16);
+    if (n > 256) n = (n + 31) / 32 * 32;
+    return n;
+}
+
+extern "C" size_t hrl_board_pack_floats(int64_t rows, int64_t K) {
+    return (size_t)((K + 31) / 32) * 2 * (size_t)hrl_gemm_padded_rows(rows) * 32;
+}
+
+extern "C" int hrl_board_pack(const float *w, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W, float *image_fwd,
+                              int32_t fwd_rows, int32_t fwd_row0, float *image_bwd, int32_t bwd_rows, int32_t bwd_k0, void *stream) {
+    HRL_REQUIRE(w && (image_fwd || image_bwd) && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && H > 0 && W > 0 && (kh & 1) && (kw & 1),
+                HRL_ERR_BAD_ARG, "hrl_board_pack: NULL pointer or bad shape (odd kernels only)");
+    HRL_REQUIRE((!image_fwd || (fwd_rows <= 288 && fwd_row0 >= 0 && fwd_row0 + Cout * H * W <= fwd_rows)) &&
+                    (!image_bwd || (bwd_rows <= 288 && bwd_rows == Cin * H * W && bwd_k0 >= 0)),
+                HRL_ERR_BAD_ARG, "hrl_board_pack: operand rows outside the packed range (<= 288)");
+    const long long n = (long long)Cout * Cin * H * W * H * W;
+    board_pack_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, Cout, Cin, kh, kw, H, W, image_fwd,
+                                                                                      hrl_gemm_padded_rows(fwd_rows), fwd_row0, image_bwd,
+                                                                                      hrl_gemm_padded_rows(bwd_rows), bwd_k0);
     HRL_CUDA_CHECK(cudaGetLastError());
     return HRL_OK;
 }

@@ -30,10 +30,10 @@ from ._capi import GEMM_EPILOGUES, HrlGemmArgs, check, lib
 from .ops import _count, _ptr, _stream_ptr
 
 
-def _operand(o, t, t2=None, consts=None, relu=False, kmajor=True, by_row=False):
+def _operand(o, t, t2=None, consts=None, relu=False, kmajor=True, by_row=False, packed=False):
     o.ptr, o.ptr2 = _ptr(t), _ptr(t2)
-    o.ld = t.stride(0)
-    o.kmajor, o.relu, o.feature_is_row = int(kmajor), int(relu), int(by_row)
+    o.ld = 0 if packed else t.stride(0)
+    o.kmajor, o.relu, o.feature_is_row, o.packed = int(kmajor), int(relu), int(by_row), int(packed)
     if consts is not None:
         o.p, o.r = _ptr(consts[0]), _ptr(consts[-1])
         o.q = _ptr(consts[1]) if len(consts) == 3 else None
@@ -78,9 +78,14 @@ class FusedBoardNet:
         self.tiles = (self.M + 127) // 128
         f = dict(dtype=torch.float32, device=device)
         M_, D = self.M, self.D
-        self.Wd0 = torch.empty((D, self.K0), **f)
-        self.Wd = [torch.empty((D, D), **f) for _ in range(self.depth)]
-        self.Wh = torch.empty((self.NH, D), **f)
+        # weights as packed B-operand images (pre-split TF32 hi/lo, pre-swizzled, one bulk copy per stage): `f` for the
+        # forward product (rows = output features), `b` for the input-gradient product (rows = input features)
+        img = lambda rows, K: torch.zeros(lib().hrl_board_pack_floats(rows, K), **f)
+        self.W0f = img(D, self.K0)
+        self.Wf = [img(D, D) for _ in range(self.depth)]
+        self.Wb = [img(D, D) for _ in range(self.depth)]
+        self.Whf = img(self.NH, D)
+        self.Whb = img(D, self.NH)
         self.b0 = torch.empty(D, **f)
         self.bh = torch.empty(self.NH, **f)
         self.A0 = torch.empty((M_, D), **f)
@@ -130,9 +135,10 @@ class FusedBoardNet:
         check(lib().hrl_gemm_fused(C.byref(g), _stream_ptr()))
         _count(2 if (splits > 1 and not partial) else 1)
 
-    def _expand(self, weight, dense, H, W):
+    def _pack(self, weight, H, W, fwd=None, fwd_rows=0, fwd_row0=0, bwd=None, bwd_rows=0, bwd_k0=0):
         Cout, Cin, kh, kw = weight.shape
-        check(lib().hrl_board_expand(_ptr(weight), _ptr(dense), Cout, Cin, kh, kw, H, W, _stream_ptr()))
+        check(lib().hrl_board_pack(_ptr(weight), Cout, Cin, kh, kw, H, W, _ptr(fwd), fwd_rows, fwd_row0, _ptr(bwd), bwd_rows, bwd_k0,
+                                   _stream_ptr()))
         _count()
 
     def _fold(self, partials, splits, stride, grad, H, W):
@@ -164,29 +170,29 @@ class FusedBoardNet:
         self.H, self.W = H, W
         self.x2d = x.view(M_, self.K0)
         with torch.no_grad():
-            self._expand(m.stem.weight, self.Wd0, H, W)
+            self._pack(m.stem.weight, H, W, fwd=self.W0f, fwd_rows=D)
             for l, blk in enumerate(m.tower):
-                self._expand(blk[0].weight, self.Wd[l], H, W)
-            self._expand(m.p_squeeze.weight, self.Wh[:self.pmaps * self.cells], H, W)
-            self._expand(m.v_squeeze.weight, self.Wh[self.pmaps * self.cells:(self.pmaps + self.vmaps) * self.cells], H, W)
-            if self.rmaps:
-                self._expand(m.r_squeeze.weight, self.Wh[(self.pmaps + self.vmaps) * self.cells:], H, W)
+                self._pack(blk[0].weight, H, W, fwd=self.Wf[l], fwd_rows=D, bwd=self.Wb[l], bwd_rows=D)
+            heads = [(m.p_squeeze, 0), (m.v_squeeze, self.pmaps * self.cells)] + \
+                ([(m.r_squeeze, (self.pmaps + self.vmaps) * self.cells)] if self.rmaps else [])
+            for sq_, row0 in heads:       # the squeeze convolutions side by side in ONE operand
+                self._pack(sq_.weight, H, W, fwd=self.Whf, fwd_rows=self.NH, fwd_row0=row0, bwd=self.Whb, bwd_rows=D, bwd_k0=row0)
             self.b0.view(self.width, self.cells).copy_(m.stem.bias.view(-1, 1).expand(self.width, self.cells))
             sq = [m.p_squeeze.bias, m.v_squeeze.bias] + ([m.r_squeeze.bias] if self.rmaps else [])
             self.bh.view(-1, self.cells).copy_(torch.cat(sq).view(-1, 1).expand(-1, self.cells))
             # stem: bias + ReLU in the epilogue
-            self._gemm(dict(t=self.x2d), dict(t=self.Wd0), self.A0, K=self.K0, N=D, bias=self.b0, epilogue='relu')
+            self._gemm(dict(t=self.x2d), dict(t=self.W0f, packed=True), self.A0, K=self.K0, N=D, bias=self.b0, epilogue='relu')
             src = dict(t=self.A0)
             for l, blk in enumerate(m.tower):
                 bnm, st = blk[1], self.bn[l]
-                self._gemm(src, dict(t=self.Wd[l]), self.Y[l], K=D, N=D, epilogue='stats')
+                self._gemm(src, dict(t=self.Wf[l], packed=True), self.Y[l], K=D, N=D, epilogue='stats')
                 check(lib().hrl_bn_finalize_fwd(_ptr(self.cp), self.tiles, self.width, self.cells, M_, _ptr(bnm.weight), _ptr(bnm.bias),
                                                 float(bnm.eps), float(bnm.momentum), _ptr(bnm.running_mean), _ptr(bnm.running_var),
                                                 _ptr(bnm.num_batches_tracked), _ptr(st['mean']), _ptr(st['rstd']), _ptr(st['scale']),
                                                 _ptr(st['shift']), _stream_ptr()))
                 _count()
                 src = dict(t=self.Y[l], consts=(st['scale'], st['shift']), relu=True)
-            self._gemm(src, dict(t=self.Wh), self.Hpre, K=D, N=self.NH, bias=self.bh)
+            self._gemm(src, dict(t=self.Whf, packed=True), self.Hpre, K=D, N=self.NH, bias=self.bh)
             check(lib().hrl_heads_fwd(_ptr(self.Hpre), self.ldh, M_, self.cells, self.pmaps, self.vmaps, self.rmaps, self.A, self.slope,
                                       _ptr(m.p_out.weight), _ptr(m.v_out.weight), _ptr(m.r_out.weight) if self.rmaps else None,
                                       _ptr(self.policy), _ptr(self.value), _ptr(self.ret), _stream_ptr()))
@@ -219,7 +225,7 @@ class FusedBoardNet:
             if self.rmaps:
                 heads.append((g(m.r_squeeze.weight), (self.pmaps + self.vmaps) * self.cells))
             self._wgrad(dict(t=self.dHpre, kmajor=False), dict(a_top, kmajor=False, by_row=True), self.NH, D, 'heads', heads, H, W)
-            self._gemm(dict(t=self.dHpre), dict(t=self.Wh, kmajor=False), self.dZ[L - 1], K=self.NH, N=D, epilogue='mask_stats',
+            self._gemm(dict(t=self.dHpre), dict(t=self.Whb, packed=True), self.dZ[L - 1], K=self.NH, N=D, epilogue='mask_stats',
                        ep=dict(y=self.Y[L - 1], scale=top['scale'], shift=top['shift'], mean=top['mean'], rstd=top['rstd']))
             for l in range(L - 1, -1, -1):
                 blk, st = m.tower[l], self.bn[l]
@@ -237,10 +243,10 @@ class FusedBoardNet:
                 self._wgrad(dict(dy, kmajor=False, by_row=True), dict(a_in, kmajor=False, by_row=True), D, D, 'tower',
                             [(g(blk[0].weight), 0)], H, W)
                 if l > 0:
-                    self._gemm(dy, dict(t=self.Wd[l], kmajor=False), self.dZ[l - 1], K=D, N=D, epilogue='mask_stats',
+                    self._gemm(dy, dict(t=self.Wb[l], packed=True), self.dZ[l - 1], K=D, N=D, epilogue='mask_stats',
                                ep=dict(y=self.Y[l - 1], scale=below['scale'], shift=below['shift'], mean=below['mean'], rstd=below['rstd']))
                 else:
-                    self._gemm(dy, dict(t=self.Wd[0], kmajor=False), self.dZ0, K=D, N=D, epilogue='mask_stats', ep=dict(y=self.A0))
+                    self._gemm(dy, dict(t=self.Wb[0], packed=True), self.dZ0, K=D, N=D, epilogue='mask_stats', ep=dict(y=self.A0))
             # stem: bias gradient from the column sums of dZ0, weight gradient over the raw observations
             check(lib().hrl_bn_finalize_bwd(_ptr(self.cp), self.tiles, self.width, self.cells, M_, None, None, None, None,
                                             _ptr(g(m.stem.bias)), None, None, None, _stream_ptr()))

@@ -228,6 +228,8 @@ typedef struct HrlGemmOperand {
     int32_t kmajor;              /* 1: element (row,k) at row*ld + k; 0: at k*ld + row                 */
     int32_t relu;
     int32_t feature_is_row;
+    int32_t packed;              /* B only: ptr is an hrl_board_pack image (weights pre-split into TF32 hi/lo halves and
+                                    pre-swizzled, one contiguous block per 32-element chunk: staged by ONE bulk copy)  */
 } HrlGemmOperand;
 
 typedef enum { HRL_GEMM_EP_STORE = 0, HRL_GEMM_EP_RELU = 1, HRL_GEMM_EP_STATS = 2, HRL_GEMM_EP_MASK_STATS = 3 } HrlGemmEpilogue;
@@ -286,6 +288,18 @@ int hrl_heads_bwd(const float *pre, int64_t ld, int64_t M, int32_t cells, int32_
  */
 int hrl_board_expand(const float *w, float *dense, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W,
                      void *stream);
+/*
+ * hrl_board_pack: the same dense matrix, written directly as the B-operand images of hrl_gemm_fused (HrlGemmOperand.packed)
+ * for the forward product (rows = output features (o,q), reduction = input features (i,p)) and for the input-gradient
+ * product (rows = input features, reduction = output features).  Image layout: [chunk of 32 reduction elements][hi | lo]
+ * [n_pad rows][128 bytes, 16-byte slots XOR-swizzled by the row], n_pad = hrl_gemm_padded_rows(rows of the operand);
+ * row0 / k0 place several convolutions side by side in one operand (e.g. the policy / value squeeze convolutions).
+ * Padding rows and the reduction tail must be zero: zero the images once, they are never written.
+ */
+int32_t hrl_gemm_padded_rows(int64_t N);
+size_t hrl_board_pack_floats(int64_t rows, int64_t K);      /* floats of an image with `rows` operand rows over K */
+int hrl_board_pack(const float *w, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W, float *image_fwd,
+                   int32_t fwd_rows, int32_t fwd_row0, float *image_bwd, int32_t bwd_rows, int32_t bwd_k0, void *stream);
 int hrl_board_fold(const float *ddense, int32_t splits, int64_t split_stride, float *dw, int32_t Cout, int32_t Cin, int32_t kh,
                    int32_t kw, int32_t H, int32_t W, void *stream);
 

@@ -28,6 +28,7 @@ def timeit(fn, reps=20):
         e1.record(side); side.synchronize()
     return e0.elapsed_time(e1) / (5 * reps) * 1e3
 
+Wf, Wb = eng.Wf[0], eng.Wb[0]      # packed images (contents irrelevant for timing)
 ep_full = dict(y=Y, scale=c[0], shift=c[1], mean=c[2], rstd=c[3])
 cases = {
     'fwd plain': lambda: eng._gemm(dict(t=X), dict(t=W), out, K=D, N=D),
@@ -35,6 +36,11 @@ cases = {
     'fwd stats epilogue': lambda: eng._gemm(dict(t=X), dict(t=W), out, K=D, N=D, epilogue='stats'),
     'fwd A affine+relu': lambda: eng._gemm(dict(t=X, consts=(c[0], c[1]), relu=True), dict(t=W), out, K=D, N=D),
     'fwd A affine+relu + stats': lambda: eng._gemm(dict(t=X, consts=(c[0], c[1]), relu=True), dict(t=W), out, K=D, N=D, epilogue='stats'),
+    'fwd packed B': lambda: eng._gemm(dict(t=X), dict(t=Wf, packed=True), out, K=D, N=D),
+    'fwd packed B, A affine+relu + stats': lambda: eng._gemm(dict(t=X, consts=(c[0], c[1]), relu=True), dict(t=Wf, packed=True), out, K=D, N=D,
+                                                              epilogue='stats'),
+    'dgrad packed B, 2-source + mask_stats': lambda: eng._gemm(dict(t=X, t2=Y, consts=(c[0], c[1], c[2])), dict(t=Wb, packed=True), out, K=D,
+                                                                N=D, epilogue='mask_stats', ep=ep_full),
     'dgrad plain': lambda: eng._gemm(dict(t=X), dict(t=W, kmajor=False), out, K=D, N=D),
     'dgrad A 2-source': lambda: eng._gemm(dict(t=X, t2=Y, consts=(c[0], c[1], c[2])), dict(t=W, kmajor=False), out, K=D, N=D),
     'dgrad A 2-source + mask_stats': lambda: eng._gemm(dict(t=X, t2=Y, consts=(c[0], c[1], c[2])), dict(t=W, kmajor=False), out, K=D, N=D,
@@ -45,7 +51,7 @@ cases = {
                                                 dict(t=Y, consts=(c[3], c[4]), relu=True, kmajor=False, by_row=True), None, K=M, N=D, M=D,
                                                 splits=eng.splits['tower'], partial=True),
 }
-for k, fn in cases.items():
-    print('%-36s %6.1f us' % (k, timeit(fn)))
+for k, fn in (cases.items() if __name__ == "__main__" else ()):
+    print('%-40s %6.1f us' % (k, timeit(fn)))
 g = torch.empty(32, 32, 3, 3, device='cuda')
 print('%-36s %6.1f us' % ('fold (48 slices)', timeit(lambda: eng._fold(eng.ws, eng.splits['tower'], D * D, g, 3, 3))))

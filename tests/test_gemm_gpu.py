@@ -65,3 +65,41 @@ def test_gemm_non_contiguous_leading_dimensions_and_output_view():
     want = a.double() @ b.double().t()
     assert (out.double() - want).abs().max().item() < 2e-6 * (a.double().abs() @ b.double().abs().t()).max().item()
     assert out_big[:, :16].abs().max().item() == 0 and out_big[:, 16 + 288:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize('Cout,Cin,H,W,ksz,M', [(32, 32, 3, 3, 3, 1000), (32, 3, 3, 3, 3, 515), (2, 32, 3, 3, 1, 300), (8, 5, 4, 4, 3, 129)])
+def test_packed_weight_images_forward_and_input_gradient(Cout, Cin, H, W, ksz, M):
+    """hrl_board_pack writes a convolution over the board as the GEMM's packed B operand (pre-split, pre-swizzled, one bulk
+    copy per stage): both images (forward / input gradient) must give the products of the float64 convolution."""
+    import ctypes as C
+    from handyrl_b200._capi import HrlGemmArgs, check, lib
+    from handyrl_b200.ops import _ptr, _stream_ptr
+    g = torch.Generator(device='cuda').manual_seed(Cout * 100 + Cin)
+    w = torch.randn(Cout, Cin, ksz, ksz, device='cuda', generator=g)
+    x = torch.randn(M, Cin, H, W, device='cuda', generator=g)
+    dy = torch.randn(M, Cout, H, W, device='cuda', generator=g)
+    row0 = 7 if Cout * H * W + 7 <= 288 else 0                  # forward operand shared with another (absent) convolution
+    rows_f, rows_b = Cout * H * W + row0, Cin * H * W
+    fwd = torch.zeros(lib().hrl_board_pack_floats(rows_f, rows_b), device='cuda')
+    bwd = torch.zeros(lib().hrl_board_pack_floats(rows_b, rows_f), device='cuda')
+    check(lib().hrl_board_pack(_ptr(w), Cout, Cin, ksz, ksz, H, W, _ptr(fwd), rows_f, row0, _ptr(bwd), rows_b, row0, _stream_ptr()))
+
+    def product(a, image, N, K):
+        out = torch.empty(M, N, device='cuda')
+        args = HrlGemmArgs()
+        args.a.ptr, args.a.ld, args.a.kmajor = _ptr(a), a.stride(0), 1
+        args.b.ptr, args.b.kmajor, args.b.packed = _ptr(image), 1, 1
+        args.C, args.ldc, args.M, args.N, args.K, args.splits = _ptr(out), N, M, N, K, 1
+        check(lib().hrl_gemm_fused(C.byref(args), _stream_ptr()))
+        return out
+
+    xd, wd, dyd = x.double().requires_grad_(True), w.double(), dy.double()
+    ref = torch.nn.functional.conv2d(xd, wd, padding=ksz // 2)
+    ref.backward(dyd)
+    y = product(x.reshape(M, -1), fwd, rows_f, rows_b)
+    assert (y[:, :row0] == 0).all()
+    scale = torch.nn.functional.conv2d(x.double().abs(), wd.abs(), padding=ksz // 2).max().item()
+    assert (y[:, row0:].double() - ref.reshape(M, -1)).abs().max().item() <= 2e-6 * scale
+    dyp = torch.cat([torch.randn(M, row0, device='cuda', generator=g), dy.reshape(M, -1)], 1).contiguous()      # garbage under the absent rows
+    dx = product(dyp, bwd, rows_b, rows_f)
+    assert (dx.double() - xd.grad.reshape(M, -1)).abs().max().item() <= 2e-6 * xd.grad.abs().max().item() * 9 * Cout
