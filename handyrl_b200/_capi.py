@@ -113,6 +113,7 @@ SYMBOLS = {
     'hrl_heads_num_blocks': (C.c_int32, [C.c_int64]),
     'hrl_heads_fwd': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_int32] * 5 + [C.c_float] + [C.c_void_p] * 7),
     'hrl_heads_bwd': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_int32] * 5 + [C.c_float] + [C.c_void_p] * 16),
+    'hrl_gemm_set_debug': (None, [C.c_int]),
     'hrl_gemm_padded_rows': (C.c_int32, [C.c_int64]),
     'hrl_board_pack_floats': (C.c_size_t, [C.c_int64, C.c_int64]),
     'hrl_board_pack': (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

@@ -29,6 +29,10 @@
 
 #include "common.cuh"
 
+// profiling / test hook (include/hrl_b200.h): 1 = no MMAs, 2 = no operand loads, +64 = A operand never staged through shared memory
+static int g_gemm_debug = 0;
+extern "C" void hrl_gemm_set_debug(int v) { g_gemm_debug = v; }
+
 namespace hrl {
 
 constexpr int kGemmThreads = 512;          // producer / epilogue threads (16 warps)
@@ -244,8 +248,12 @@ constexpr int kAColBase = 288;      // TMEM columns: accumulator [0, 288), A sta
 // 72 cycles while the producers wrote the next stage), see profiles/README.md.
 // A thread owns ONE row of the A tile (its TMEM lane: warp w may only touch lanes 32 (w % 4) ... + 31) and 8 of the 32
 // reduction elements of a chunk (warp group w / 4).
-template <bool A_K, bool B_K, int ITEMS_A, int ITEMS_B, bool PACKED>
+// PACKED_MODE 0: B through registers; 1: B = packed image (bulk copies); 2: ... and A staged through shared memory by cp.async
+// (needs 16-byte aligned A rows; two stages instead of three: the raw A tiles take the room of the third)
+template <bool A_K, bool B_K, int ITEMS_A, int ITEMS_B, int PACKED_MODE>
 __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmParams p, const int n_pad) {
+    constexpr bool PACKED = PACKED_MODE != 0, STAGED_A = PACKED_MODE == 2;
+    constexpr int NS = STAGED_A ? 2 : kStages;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // swizzle atoms need 1024-byte alignment
     __shared__ __align__(8) uint64_t bars[2 * kStages + 1];      // full[kStages] | empty[kStages] | accumulator done
@@ -329,34 +337,26 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
         // ---- the MMA warp: waits for a stage to be full, issues its 3 x 4 (x halves) products, commits them to the
         //      stage's "empty" barrier (and the last ones to the accumulator barrier).  It never touches operand data.
         for (int c = c_begin; c < c_end; c++) {
-            const int it = c - c_begin, s = it % kStages;
-            mbar_wait(smem_u32(&bars[s]), (it / kStages) & 1);
+            const int it = c - c_begin, s = it % NS;
+            mbar_wait(smem_u32(&bars[s]), (it / NS) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 if ((p.debug & 3) != 1) {
                     const uint32_t st = smem_base + s * stage_bytes;
                     const uint32_t b_hi = st, b_lo = st + b_bytes;
                     const uint32_t a_hi = tmem_base + kAColBase + 64 * s, a_lo = a_hi + 32;
-                    // EXPERIMENT (profiling knob >> 2): how the 288 accumulator columns are cut into instructions
-                    int seg_n[3] = {n_mma, n_mma, 0}, nseg = halves;
-                    const int mode = p.debug >> 2;
-                    if (mode == 1) { seg_n[0] = 256; seg_n[1] = n_pad - 256; nseg = 2; }
-                    if (mode == 2) { seg_n[0] = 96; seg_n[1] = 96; seg_n[2] = n_pad - 192; nseg = 3; }
-                    if (mode == 3) { seg_n[0] = 192; seg_n[1] = n_pad - 192; nseg = 2; }
-                    if (mode == 4) { seg_n[0] = 128; seg_n[1] = 128; seg_n[2] = n_pad - 256; nseg = 3; }
+                    // (how the 288 columns are cut into instructions does not matter -- 144+144, 256+32, 192+96 all take 100 ns per
+                    //  k-step and product, three instructions 127 ns: ~42 ns issue floor per instruction, scripts/gemm_mma_shapes.py)
 #pragma unroll
                     for (int ks = 0; ks < kChunkK / 8; ks++) {
-                        int n_at = 0;
-                        for (int h = 0; h < nseg; h++) {
-                            const uint32_t boff = 32 * ks + n_at * 128;      // n_mma % 8 == 0: whole swizzle atoms
-                            const uint32_t d = tmem_base + n_at;
-                            const uint32_t idesc_h = umma_idesc_tf32(kTileM, seg_n[h]);
-                            n_at += seg_n[h];
+                        for (int h = 0; h < halves; h++) {
+                            const uint32_t boff = 32 * ks + h * n_mma * 128;      // n_mma % 8 == 0: whole swizzle atoms
+                            const uint32_t d = tmem_base + h * n_mma;
                             const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
                             // small terms first: a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
-                            umma_tf32_ts(d, a_lo + 8 * ks, umma_desc(b_hi + boff), idesc_h, first);
-                            umma_tf32_ts(d, a_hi + 8 * ks, umma_desc(b_lo + boff), idesc_h, 1u);
-                            umma_tf32_ts(d, a_hi + 8 * ks, umma_desc(b_hi + boff), idesc_h, 1u);
+                            umma_tf32_ts(d, a_lo + 8 * ks, umma_desc(b_hi + boff), idesc, first);
+                            umma_tf32_ts(d, a_hi + 8 * ks, umma_desc(b_lo + boff), idesc, 1u);
+                            umma_tf32_ts(d, a_hi + 8 * ks, umma_desc(b_hi + boff), idesc, 1u);
                         }
                     }
                 }
@@ -394,14 +394,57 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
                     }
             }
         };
-        if (PACKED && c_begin < c_end) load_a(c_begin, xa, ya);
+        // STAGED_A: the chunk's A rows come through shared memory.  (Read straight from global memory a warp -- 32 rows,
+        // the lanes of tensor memory -- touches 32 cache lines per load instruction, 8x the wavefronts of a coalesced copy:
+        // that was what bound the producers, 0.55 us per chunk and source.)  cp.async copies them coalesced (8 lanes = one
+        // row's 128 bytes) one chunk ahead into [2 stages][2 sources][128 rows][144 bytes]; a thread then reads its row's
+        // 32 bytes (rows 144 bytes apart: 4 wavefronts per 512-byte request, the minimum).
+        constexpr int kRawLd = 36;
+        float *rawA = reinterpret_cast<float *>(smem + NS * stage_bytes);
+        auto issue_a = [&](int c) {
+            const int k0 = c * kChunkK, k_left = p.K - k0;
+            const int st = (c - c_begin) & 1;
+#pragma unroll
+            for (int u = 0; u < kTileM * 8 / kGemmThreads; u++) {
+                const int idx = tid + u * kGemmThreads, row = idx >> 3, j = idx & 7;
+                int bytes = row < rows_a ? (k_left - 4 * j) * 4 : 0;
+                bytes = max(0, min(16, bytes));
+                const long long off = bytes > 0 ? (long long)(m0 + row) * p.a.ld + k0 + 4 * j : 0;
+                const uint32_t dst = smem_u32(rawA + ((st * 2 + 0) * kTileM + row) * kRawLd + 4 * j);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(p.a.ptr + off), "r"(bytes) : "memory");
+                if (p.a.ptr2)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + kTileM * kRawLd * 4), "l"(p.a.ptr2 + off), "r"(bytes)
+                                 : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (STAGED_A) {
+            if (c_begin < c_end) issue_a(c_begin);
+        } else if (PACKED && c_begin < c_end) {
+            load_a(c_begin, xa, ya);
+        }
         for (int c = c_begin; c < c_end; c++) {
-            const int it = c - c_begin, s = it % kStages;
+            const int it = c - c_begin, s = it % NS;
             const int k0 = c * kChunkK;
             const int k_left = p.K - k0;
             const long long adv_b = B_K ? (long long)k0 : (long long)k0 * p.b.ld;
             float4 vb[ITEMS_B];
-            if (PACKED) {
+            if (STAGED_A) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");               // my copies of this chunk have landed ...
+                asm volatile("bar.sync 1, %0;" ::"n"(kGemmThreads) : "memory");    // ... everybody's; and the other raw stage is free
+                if (c + 1 < c_end) issue_a(c + 1);
+                const float *ra = rawA + (((it & 1) * 2 + 0) * kTileM + a_row) * kRawLd + a_k;
+                const float4 u0 = reinterpret_cast<const float4 *>(ra)[0], u1 = reinterpret_cast<const float4 *>(ra)[1];
+                xa[0] = u0.x; xa[1] = u0.y; xa[2] = u0.z; xa[3] = u0.w; xa[4] = u1.x; xa[5] = u1.y; xa[6] = u1.z; xa[7] = u1.w;
+                if (p.a.ptr2) {
+                    const float4 w0 = reinterpret_cast<const float4 *>(ra + kTileM * kRawLd)[0],
+                                 w1 = reinterpret_cast<const float4 *>(ra + kTileM * kRawLd)[1];
+                    ya[0] = w0.x; ya[1] = w0.y; ya[2] = w0.z; ya[3] = w0.w; ya[4] = w1.x; ya[5] = w1.y; ya[6] = w1.z; ya[7] = w1.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) ya[e] = 0.f;
+                }
+            } else if (PACKED) {
                 if (c + 1 < c_end) load_a(c + 1, xn, yn);        // next chunk's A in flight while this one is processed
             } else {
                 load_a(c, xa, ya);                               // (B staged through registers: no room for a second A set)
@@ -471,7 +514,7 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
                     }
                 }
             }
-            if (it >= kStages) mbar_wait(smem_u32(&bars[kStages + s]), ((it / kStages) - 1) & 1);      // the MMAs that read this stage are done
+            if (it >= NS) mbar_wait(smem_u32(&bars[kStages + s]), ((it / NS) - 1) & 1);      // the MMAs that read this stage are done
             if (PACKED && tid == 0) {           // weights: one bulk copy of the stage's pre-split, pre-swizzled image
                 const uint32_t bar = smem_u32(&bars[s]);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(stage_bytes) : "memory");
@@ -506,7 +549,7 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[s])) : "memory");      // this stage is full
-            if (PACKED) {
+            if (PACKED && !STAGED_A) {
 #pragma unroll
                 for (int e = 0; e < 8; e++) { xa[e] = xn[e]; ya[e] = yn[e]; }
             }
@@ -686,8 +729,6 @@ __global__ void sum_partials_kernel(const float *__restrict__ partials, int spli
 
 }  // namespace hrl
 
-static int g_gemm_debug = 0;
-extern "C" void hrl_gemm_set_debug(int v) { g_gemm_debug = v; }
 
 extern "C" size_t hrl_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int32_t splits) {
     (void)K;
@@ -751,14 +792,17 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
     p.ep_y = g.ep_y; p.ep_ldy = g.ep_ldy;
     p.ep_scale = g.ep_scale; p.ep_shift = g.ep_shift; p.ep_mean = g.ep_mean; p.ep_rstd = g.ep_rstd;
     p.col_partials = g.col_partials;
-    p.debug = g_gemm_debug;
+    p.debug = g_gemm_debug & 63;
     splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;      // no empty slices
     if (splits > 1) {
         p.C = g.workspace; p.ldc = N; p.c_split_stride = M * N;
     } else {
         p.C = g.C; p.ldc = g.ldc; p.c_split_stride = 0;
     }
-    size_t smem_bytes = 1024 + (size_t)kStages * (2 * (size_t)n_pad * kChunkK * 4);
+    const bool staged_a = !(g_gemm_debug & 64) && g.b.packed && g.a.kmajor && g.a.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(g.a.ptr) & 15) == 0 &&
+                          (g.a.ptr2 == nullptr || (reinterpret_cast<uintptr_t>(g.a.ptr2) & 15) == 0);
+    size_t smem_bytes = staged_a ? 1024 + 2 * (2 * (size_t)n_pad * kChunkK * 4) + 2 * 2 * (size_t)kTileM * 36 * 4
+                                 : 1024 + (size_t)kStages * (2 * (size_t)n_pad * kChunkK * 4);
     const size_t red_rows = (size_t)kGemmThreads / (size_t)((n_pad - 12) / 4 > 0 ? (n_pad - 12) / 4 : 1);      // copy-out row passes (as the kernel)
     const size_t ep_bytes = 1024 + ((size_t)kTileM * (n_pad + 4) + 2 * red_rows * (size_t)n_pad) * 4;      // epilogue tile + column-sum scratch
     if (smem_bytes < ep_bytes) smem_bytes = ep_bytes;
@@ -771,7 +815,7 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
                                             (int)smem_bytes));                                                            \
         gemm_tf32x3_kernel<AK, BK, IA, IB, PK><<<grid, kGemmBlock, smem_bytes, stream>>>(p, n_pad);                      \
     }
-#define HRL_GEMM_LAUNCH2(AK, BK, IB) HRL_GEMM_LAUNCH3(AK, BK, IB, false)
+#define HRL_GEMM_LAUNCH2(AK, BK, IB) HRL_GEMM_LAUNCH3(AK, BK, IB, 0)
 #define HRL_GEMM_LAUNCH(IB)                                                                    \
     {                                                                                         \
         if (p.a.kmajor && p.b.kmajor) HRL_GEMM_LAUNCH2(true, true, IB)                        \
@@ -779,9 +823,10 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
         else if (p.b.kmajor) HRL_GEMM_LAUNCH2(false, true, IB)                                \
         else HRL_GEMM_LAUNCH2(false, false, IB)                                               \
     }
-    if (p.b.packed) {
-        if (p.a.kmajor) HRL_GEMM_LAUNCH3(true, true, 1, true)
-        else HRL_GEMM_LAUNCH3(false, true, 1, true)
+    if (staged_a) HRL_GEMM_LAUNCH3(true, true, 1, 2)
+    else if (p.b.packed) {
+        if (p.a.kmajor) HRL_GEMM_LAUNCH3(true, true, 1, 1)
+        else HRL_GEMM_LAUNCH3(false, true, 1, 1)
     } else if (items_b <= 1) HRL_GEMM_LAUNCH(1)
     else if (items_b <= 3) HRL_GEMM_LAUNCH(3)
     else HRL_GEMM_LAUNCH(5)

@@ -296,6 +296,11 @@ int hrl_board_expand(const float *w, float *dense, int32_t Cout, int32_t Cin, in
  * row0 / k0 place several convolutions side by side in one operand (e.g. the policy / value squeeze convolutions).
  * Padding rows and the reduction tail must be zero: zero the images once, they are never written.
  */
+/* Profiling / test hook of hrl_gemm_fused, process-global and NOT thread safe (default 0 = the product path):
+ * 1 = skip the MMAs, 2 = skip the operand loads (timing attribution, scripts/gemm_breakdown.py);
+ * +64 = read the A operand straight from global memory even where it could be staged through shared memory (the two
+ * paths must agree bit for bit: tests/test_gemm_gpu.py).  Results with 1 or 2 set are garbage by design. */
+void hrl_gemm_set_debug(int mode);
 int32_t hrl_gemm_padded_rows(int64_t N);
 size_t hrl_board_pack_floats(int64_t rows, int64_t K);      /* floats of an image with `rows` operand rows over K */
 int hrl_board_pack(const float *w, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W, float *image_fwd,

@@ -103,3 +103,48 @@ def test_packed_weight_images_forward_and_input_gradient(Cout, Cin, H, W, ksz, M
     dyp = torch.cat([torch.randn(M, row0, device='cuda', generator=g), dy.reshape(M, -1)], 1).contiguous()      # garbage under the absent rows
     dx = product(dyp, bwd, rows_b, rows_f)
     assert (dx.double() - xd.grad.reshape(M, -1)).abs().max().item() <= 2e-6 * xd.grad.abs().max().item() * 9 * Cout
+
+
+@pytest.mark.parametrize('M,N,K', [(300, 288, 288), (515, 144, 144), (515, 36, 144), (515, 144, 36), (2048, 27, 288)])
+def test_a_operand_staged_through_shared_memory_equals_direct_reads(M, N, K):
+    """With a packed B image and 16-byte aligned A rows the A tiles are copied to shared memory by cp.async, one chunk ahead,
+    instead of being read row-per-lane from global memory: same arithmetic, so every variant (plain, affine + ReLU with the
+    statistics epilogue, two sources with the masked epilogue) must agree bit for bit with the direct path (hook +64)."""
+    import ctypes as C
+    from handyrl_b200._capi import GEMM_EPILOGUES, HrlGemmArgs, check, lib
+    from handyrl_b200.ops import _ptr, _stream_ptr
+    g = torch.Generator(device='cuda').manual_seed(M + N)
+    x, x2 = torch.randn(M, K, device='cuda', generator=g), torch.randn(M, K, device='cuda', generator=g)
+    y = torch.randn(M, N, device='cuda', generator=g)
+    c3 = [torch.rand(K, device='cuda', generator=g) for _ in range(3)]
+    img = torch.randn(lib().hrl_board_pack_floats(N, K), device='cuda', generator=g)
+    cp = torch.zeros(((M + 127) // 128) * 2 * N, device='cuda')
+
+    def run(x2_, consts, relu, ep):
+        out = torch.empty(M, N, device='cuda')
+        a = HrlGemmArgs()
+        a.a.ptr, a.a.ptr2, a.a.ld, a.a.kmajor, a.a.relu = _ptr(x), _ptr(x2_), K, 1, int(relu)
+        if consts is not None:
+            a.a.p, a.a.r = _ptr(consts[0]), _ptr(consts[-1])
+            a.a.q = _ptr(consts[1]) if len(consts) == 3 else None
+        a.b.ptr, a.b.kmajor, a.b.packed = _ptr(img), 1, 1
+        a.C, a.ldc, a.M, a.N, a.K, a.splits, a.epilogue = _ptr(out), N, M, N, K, 1, GEMM_EPILOGUES[ep]
+        if ep in ('stats', 'mask_stats'):
+            a.col_partials = _ptr(cp)
+        if ep == 'mask_stats':
+            a.ep_y, a.ep_ldy = _ptr(y), N
+        check(lib().hrl_gemm_fused(C.byref(a), _stream_ptr()))
+        torch.cuda.synchronize()
+        return out, cp.clone()
+
+    vec = N % 4 == 0
+    try:
+        for x2_, consts, relu, ep in ((None, None, False, 'store'), (None, c3[:2], True, 'stats' if vec else 'relu'),
+                                      (x2, c3, False, 'mask_stats' if vec else 'store')):
+            lib().hrl_gemm_set_debug(64)
+            direct = run(x2_, consts, relu, ep)
+            lib().hrl_gemm_set_debug(0)
+            staged = run(x2_, consts, relu, ep)
+            assert torch.equal(direct[0], staged[0]) and torch.equal(direct[1], staged[1]), ep
+    finally:
+        lib().hrl_gemm_set_debug(0)
