@@ -66,6 +66,21 @@ class HrlGemmArgs(C.Structure):
                 ('ep_mean', C.c_void_p), ('ep_rstd', C.c_void_p), ('col_partials', C.c_void_p)]
 
 
+MAX_BOARD_JOBS = 8
+
+
+class HrlPackJob(C.Structure):
+    _fields_ = [('w', C.c_void_p), ('Cout', C.c_int32), ('Cin', C.c_int32), ('kh', C.c_int32), ('kw', C.c_int32), ('H', C.c_int32),
+                ('W', C.c_int32), ('image_fwd', C.c_void_p), ('fwd_rows', C.c_int32), ('fwd_row0', C.c_int32),
+                ('image_bwd', C.c_void_p), ('bwd_rows', C.c_int32), ('bwd_k0', C.c_int32), ('bias', C.c_void_p),
+                ('bias_cells', C.c_void_p)]
+
+
+class HrlFoldJob(C.Structure):
+    _fields_ = [('ddense', C.c_void_p), ('splits', C.c_int32), ('split_stride', C.c_int64), ('dw', C.c_void_p),
+                ('Cout', C.c_int32), ('Cin', C.c_int32), ('kh', C.c_int32), ('kw', C.c_int32), ('H', C.c_int32), ('W', C.c_int32)]
+
+
 class HrlWindow(C.Structure):
     _fields_ = [('first_step', C.c_int64), ('start', C.c_int32), ('end', C.c_int32),
                 ('train_start', C.c_int32), ('total', C.c_int32), ('outcome_row', C.c_int32),
@@ -118,6 +133,8 @@ SYMBOLS = {
     'hrl_board_pack_floats': (C.c_size_t, [C.c_int64, C.c_int64]),
     'hrl_board_pack': (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'hrl_board_expand': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
+    'hrl_board_pack_many': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    'hrl_board_fold_many': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'hrl_board_fold': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     'hrl_gemm_effective_splits': (C.c_int32, [C.c_int64, C.c_int32]),
     'hrl_lstm_gates_fwd': (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),

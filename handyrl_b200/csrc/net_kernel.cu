@@ -12,6 +12,8 @@
 // a Geister learner step runs them ~3,000 times, which is what made that step launch-bound).
 #include <math.h>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace hrl {
@@ -29,6 +31,12 @@ __global__ void board_expand_kernel(const float *__restrict__ w, float *__restri
     }
 }
 
+__host__ __device__ __forceinline__ int hrl_padded_rows_dev(int N) {      // == hrl_gemm_padded_rows
+    int n = (N + 15) / 16 * 16;
+    if (n > 256) n = (n + 31) / 32 * 32;
+    return n;
+}
+
 // dense element (row = (o,q), col = (i,p)) of the convolution, straight into packed B-operand images of the tcgen05 GEMM
 // (csrc/gemm_kernel.cu): image[chunk = k / 32][hi | lo][row][slot (k % 32) / 4 ^ (row & 7)][k % 4]
 __device__ __forceinline__ void pack_store(float *image, int n_pad, int row, int k, float v) {
@@ -40,28 +48,56 @@ __device__ __forceinline__ void pack_store(float *image, int n_pad, int row, int
     base[(long long)n_pad * 32] = v - hi;
 }
 
-__global__ void board_pack_kernel(const float *__restrict__ w, int Cout, int Cin, int kh, int kw, int H, int W, float *__restrict__ image_fwd,
-                                  int fwd_pad, int fwd_row0, float *__restrict__ image_bwd, int bwd_pad, int bwd_k0) {
-    const int HW = H * W;
-    const long long n = (long long)Cout * HW * Cin * HW;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+__device__ __forceinline__ void board_pack_body(const HrlPackJob &j, int block, int nblocks) {
+    const int HW = j.H * j.W, Cin = j.Cin, kh = j.kh, kw = j.kw, W = j.W;
+    const int fwd_pad = hrl_padded_rows_dev(j.fwd_rows), bwd_pad = hrl_padded_rows_dev(j.bwd_rows);
+    const long long n = (long long)j.Cout * HW * Cin * HW;
+    for (long long idx = (long long)block * blockDim.x + threadIdx.x; idx < n; idx += (long long)nblocks * blockDim.x) {
         const int col = (int)(idx % (Cin * HW)), row = (int)(idx / (Cin * HW));
         const int o = row / HW, q = row - o * HW, i = col / HW, p = col - i * HW;
         const int a = p / W - q / W + kh / 2, b = p % W - q % W + kw / 2;
-        const float v = (a >= 0 && a < kh && b >= 0 && b < kw) ? __ldg(w + ((long long)(o * Cin + i) * kh + a) * kw + b) : 0.f;
-        if (image_fwd) pack_store(image_fwd, fwd_pad, fwd_row0 + row, col, v);       // rows = output features, reduction = input features
-        if (image_bwd) pack_store(image_bwd, bwd_pad, col, bwd_k0 + row, v);          // rows = input features, reduction = output features
+        const float v = (a >= 0 && a < kh && b >= 0 && b < kw) ? __ldg(j.w + ((long long)(o * Cin + i) * kh + a) * kw + b) : 0.f;
+        if (j.image_fwd) pack_store(j.image_fwd, fwd_pad, j.fwd_row0 + row, col, v);       // rows = output features, reduction = input features
+        if (j.image_bwd) pack_store(j.image_bwd, bwd_pad, col, j.bwd_k0 + row, v);          // rows = input features, reduction = output features
     }
+    if (j.bias && j.bias_cells)          // the convolution's bias, one copy per cell (the product's per-column bias)
+        for (int idx = block * blockDim.x + threadIdx.x; idx < j.Cout * HW; idx += nblocks * blockDim.x) j.bias_cells[idx] = __ldg(j.bias + idx / HW);
+}
+
+struct PackJobs {
+    HrlPackJob job[HRL_MAX_BOARD_JOBS];
+    int first_block[HRL_MAX_BOARD_JOBS + 1];
+    int n;
+};
+
+__global__ void board_pack_kernel(const PackJobs jobs) {
+    int k = 0;
+    while (k + 1 < jobs.n && (int)blockIdx.x >= jobs.first_block[k + 1]) k++;
+    board_pack_body(jobs.job[k], blockIdx.x - jobs.first_block[k], jobs.first_block[k + 1] - jobs.first_block[k]);
 }
 
 // one CTA per output channel o: its HW rows of the dense gradient (a contiguous slab of HW * Cin*HW floats per K slice) are
 // summed over the slices with coalesced reads (fixed order -> deterministic) into shared memory, then folded onto the taps
-__global__ void board_fold_kernel(const float *__restrict__ ddense, int splits, long long split_stride, float *__restrict__ dw, int Cout,
-                                  int Cin, int kh, int kw, int H, int W) {
+struct FoldJobs {
+    HrlFoldJob job[HRL_MAX_BOARD_JOBS];
+    int first_block[HRL_MAX_BOARD_JOBS + 1];
+    int groups[HRL_MAX_BOARD_JOBS];                   // CTAs per output channel (groups of input channels)
+    int n;
+};
+
+__global__ void board_fold_kernel(const FoldJobs jobs) {
     extern __shared__ float slab[];                   // [HW][Cin*HW]; a CTA fills only the columns of its input channels
+    int jk = 0;
+    while (jk + 1 < jobs.n && (int)blockIdx.x >= jobs.first_block[jk + 1]) jk++;
+    const HrlFoldJob &J = jobs.job[jk];
+    const float *__restrict__ ddense = J.ddense;
+    float *__restrict__ dw = J.dw;
+    const int splits = J.splits, Cin = J.Cin, kh = J.kh, kw = J.kw, H = J.H, W = J.W, n_groups = jobs.groups[jk];
+    const long long split_stride = J.split_stride;
+    const int local = blockIdx.x - jobs.first_block[jk];
     const int HW = H * W, cols = Cin * HW, n = HW * cols;
-    const int o = blockIdx.x;
-    const int i_per = (Cin + gridDim.y - 1) / gridDim.y, i_lo = blockIdx.y * i_per, i_hi = min(Cin, i_lo + i_per);
+    const int o = local / n_groups, gy = local - o * n_groups;
+    const int i_per = (Cin + n_groups - 1) / n_groups, i_lo = gy * i_per, i_hi = min(Cin, i_lo + i_per);
     const int c_lo = i_lo * HW, c_n = (i_hi - i_lo) * HW;          // this CTA's column range
     const float *base = ddense + (long long)o * n;
     for (int e0 = threadIdx.x; e0 < HW * c_n; e0 += blockDim.x) {
@@ -236,36 +272,76 @@ extern "C" size_t hrl_board_pack_floats(int64_t rows, int64_t K) {
     return (size_t)((K + 31) / 32) * 2 * (size_t)hrl_gemm_padded_rows(rows) * 32;
 }
 
+extern "C" int hrl_board_pack_many(const HrlPackJob *jobs, int32_t n_jobs, void *stream) {
+    HRL_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= HRL_MAX_BOARD_JOBS, HRL_ERR_BAD_ARG, "hrl_board_pack_many: 1..%d jobs", HRL_MAX_BOARD_JOBS);
+    PackJobs pj;
+    pj.n = n_jobs;
+    pj.first_block[0] = 0;
+    for (int k = 0; k < n_jobs; k++) {
+        const HrlPackJob &j = jobs[k];
+        HRL_REQUIRE(j.w && (j.image_fwd || j.image_bwd) && j.Cout > 0 && j.Cin > 0 && j.kh > 0 && j.kw > 0 && j.H > 0 && j.W > 0 && (j.kh & 1) &&
+                        (j.kw & 1),
+                    HRL_ERR_BAD_ARG, "hrl_board_pack: NULL pointer or bad shape (odd kernels only)");
+        HRL_REQUIRE((!j.image_fwd || (j.fwd_rows <= 288 && j.fwd_row0 >= 0 && j.fwd_row0 + j.Cout * j.H * j.W <= j.fwd_rows)) &&
+                        (!j.image_bwd || (j.bwd_rows <= 288 && j.bwd_rows == j.Cin * j.H * j.W && j.bwd_k0 >= 0)),
+                    HRL_ERR_BAD_ARG, "hrl_board_pack: operand rows outside the packed range (<= 288)");
+        HRL_REQUIRE((j.bias == nullptr) == (j.bias_cells == nullptr), HRL_ERR_BAD_ARG, "hrl_board_pack: bias and bias_cells go together");
+        pj.job[k] = j;
+        const long long n = (long long)j.Cout * j.Cin * j.H * j.W * j.H * j.W;
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > 2 * kNumSM) blocks = 2 * kNumSM;
+        pj.first_block[k + 1] = pj.first_block[k] + blocks;
+    }
+    board_pack_kernel<<<pj.first_block[n_jobs], 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pj);
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
+
 extern "C" int hrl_board_pack(const float *w, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W, float *image_fwd,
                               int32_t fwd_rows, int32_t fwd_row0, float *image_bwd, int32_t bwd_rows, int32_t bwd_k0, void *stream) {
-    HRL_REQUIRE(w && (image_fwd || image_bwd) && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && H > 0 && W > 0 && (kh & 1) && (kw & 1),
-                HRL_ERR_BAD_ARG, "hrl_board_pack: NULL pointer or bad shape (odd kernels only)");
-    HRL_REQUIRE((!image_fwd || (fwd_rows <= 288 && fwd_row0 >= 0 && fwd_row0 + Cout * H * W <= fwd_rows)) &&
-                    (!image_bwd || (bwd_rows <= 288 && bwd_rows == Cin * H * W && bwd_k0 >= 0)),
-                HRL_ERR_BAD_ARG, "hrl_board_pack: operand rows outside the packed range (<= 288)");
-    const long long n = (long long)Cout * Cin * H * W * H * W;
-    board_pack_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, Cout, Cin, kh, kw, H, W, image_fwd,
-                                                                                      hrl_gemm_padded_rows(fwd_rows), fwd_row0, image_bwd,
-                                                                                      hrl_gemm_padded_rows(bwd_rows), bwd_k0);
+    HrlPackJob j;
+    memset(&j, 0, sizeof(j));
+    j.w = w; j.Cout = Cout; j.Cin = Cin; j.kh = kh; j.kw = kw; j.H = H; j.W = W;
+    j.image_fwd = image_fwd; j.fwd_rows = fwd_rows; j.fwd_row0 = fwd_row0;
+    j.image_bwd = image_bwd; j.bwd_rows = bwd_rows; j.bwd_k0 = bwd_k0;
+    return hrl_board_pack_many(&j, 1, stream);
+}
+
+extern "C" int hrl_board_fold_many(const HrlFoldJob *jobs, int32_t n_jobs, void *stream) {
+    HRL_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= HRL_MAX_BOARD_JOBS, HRL_ERR_BAD_ARG, "hrl_board_fold_many: 1..%d jobs", HRL_MAX_BOARD_JOBS);
+    FoldJobs fj;
+    fj.n = n_jobs;
+    fj.first_block[0] = 0;
+    size_t slab_max = 0;
+    for (int k = 0; k < n_jobs; k++) {
+        const HrlFoldJob &j = jobs[k];
+        HRL_REQUIRE(j.ddense && j.dw && j.splits >= 1 && j.Cout > 0 && j.Cin > 0 && j.kh > 0 && j.kw > 0 && j.H > 0 && j.W > 0 && (j.kh & 1) &&
+                        (j.kw & 1),
+                    HRL_ERR_BAD_ARG, "hrl_board_fold: NULL pointer or bad shape (odd kernels only)");
+        const size_t slab_bytes = (size_t)j.H * j.W * j.Cin * j.H * j.W * sizeof(float);
+        HRL_REQUIRE(slab_bytes <= 200 * 1024, HRL_ERR_UNSUPPORTED, "hrl_board_fold: Cin*(H*W)^2 = %zu floats exceed shared memory",
+                    slab_bytes / sizeof(float));
+        if (slab_bytes > slab_max) slab_max = slab_bytes;
+        fj.job[k] = j;
+        int groups = (2 * kNumSM + j.Cout - 1) / j.Cout;       // (output channel, group of input channels) CTAs: about two per SM
+        if (groups > j.Cin) groups = j.Cin;
+        fj.groups[k] = groups;
+        fj.first_block[k + 1] = fj.first_block[k] + j.Cout * groups;
+    }
+    if (slab_max > 48 * 1024)
+        HRL_CUDA_CHECK(cudaFuncSetAttribute(board_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab_max));
+    board_fold_kernel<<<fj.first_block[n_jobs], 512, slab_max, reinterpret_cast<cudaStream_t>(stream)>>>(fj);
     HRL_CUDA_CHECK(cudaGetLastError());
     return HRL_OK;
 }
 
 extern "C" int hrl_board_fold(const float *ddense, int32_t splits, int64_t split_stride, float *dw, int32_t Cout, int32_t Cin, int32_t kh,
                               int32_t kw, int32_t H, int32_t W, void *stream) {
-    HRL_REQUIRE(ddense && dw && splits >= 1 && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && H > 0 && W > 0 && (kh & 1) && (kw & 1),
-                HRL_ERR_BAD_ARG, "hrl_board_fold: NULL pointer or bad shape (odd kernels only)");
-    const size_t slab_bytes = (size_t)H * W * Cin * H * W * sizeof(float);
-    HRL_REQUIRE(slab_bytes <= 200 * 1024, HRL_ERR_UNSUPPORTED, "hrl_board_fold: Cin*(H*W)^2 = %zu floats exceed shared memory",
-                slab_bytes / sizeof(float));
-    if (slab_bytes > 48 * 1024)
-        HRL_CUDA_CHECK(cudaFuncSetAttribute(board_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab_bytes));
-    int groups = (2 * kNumSM + Cout - 1) / Cout;       // (output channel, group of input channels) CTAs: about two per SM
-    if (groups > Cin) groups = Cin;
-    board_fold_kernel<<<dim3(Cout, groups), 512, slab_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(ddense, splits, split_stride, dw, Cout,
-                                                                                                    Cin, kh, kw, H, W);
-    HRL_CUDA_CHECK(cudaGetLastError());
-    return HRL_OK;
+    HrlFoldJob j;
+    memset(&j, 0, sizeof(j));
+    j.ddense = ddense; j.splits = splits; j.split_stride = split_stride; j.dw = dw;
+    j.Cout = Cout; j.Cin = Cin; j.kh = kh; j.kw = kw; j.H = H; j.W = W;
+    return hrl_board_fold_many(&j, 1, stream);
 }
 
 extern "C" int hrl_lstm_gates_fwd(const float *gates, const float *c_prev, float *h_out, float *c_out, int64_t N, int32_t C, int32_t S,

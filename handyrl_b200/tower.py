@@ -26,7 +26,7 @@ import ctypes as C
 import torch
 
 from . import _capi, nets
-from ._capi import GEMM_EPILOGUES, HrlGemmArgs, check, lib
+from ._capi import GEMM_EPILOGUES, MAX_BOARD_JOBS, HrlFoldJob, HrlGemmArgs, HrlPackJob, check, lib
 from .ops import _count, _ptr, _stream_ptr
 
 
@@ -103,19 +103,23 @@ class FusedBoardNet:
         n_out = self.A * self.pmaps * self.cells + (self.vmaps + self.rmaps) * self.cells + self.pmaps + self.vmaps + self.rmaps
         self.heads_ws = torch.empty(lib().hrl_heads_num_blocks(M_) * n_out, **f)
         # weight-gradient products: split over samples so that (row tiles x slices) fills the GPU
-        self.splits = {}
-        self.ws = None
+        # (each product keeps its slice partials in a region of its own: ALL of them are folded onto the convolution
+        #  weights by one launch at the end of the backward pass)
+        self.splits, self.ws_at = {}, {}
         ws_floats = 0
-        for name, rows, colsn in (('stem', D, self.K0), ('tower', D, D), ('heads', self.NH, D)):
+        for name, rows, colsn, count in (('stem', D, self.K0, 1), ('tower', D, D, self.depth), ('heads', self.NH, D, 1)):
             tiles = ((rows + 127) // 128) * ((colsn + 287) // 288)
             s = lib().hrl_gemm_effective_splits(M_, max(1, min(M_ // 64, 148 // tiles)))
             self.splits[name] = s
-            ws_floats = max(ws_floats, s * rows * colsn)
+            for i in range(count):
+                self.ws_at[(name, i)] = ws_floats
+                ws_floats += s * rows * colsn
         self.ws = torch.empty(ws_floats, **f)
+        self.fold_jobs = []
         self.slope = 0.1
 
     # ------------------------------------------------------------------ helpers
-    def _gemm(self, a, b, out, K, N, M=None, bias=None, epilogue='store', splits=1, partial=False, ep=None):
+    def _gemm(self, a, b, out, K, N, M=None, bias=None, epilogue='store', splits=1, partial=False, ep=None, ws=None):
         g = HrlGemmArgs()
         _operand(g.a, **a)
         _operand(g.b, **b)
@@ -125,7 +129,7 @@ class FusedBoardNet:
         g.M, g.N, g.K = (self.M if M is None else M), N, K
         g.splits = splits
         g.epilogue = GEMM_EPILOGUES[epilogue]
-        g.workspace = _ptr(self.ws) if splits > 1 else None
+        g.workspace = _ptr(ws) if splits > 1 else None
         if epilogue in ('stats', 'mask_stats'):
             g.col_partials = _ptr(self.cp)
         if ep is not None:
@@ -135,30 +139,45 @@ class FusedBoardNet:
         check(lib().hrl_gemm_fused(C.byref(g), _stream_ptr()))
         _count(2 if (splits > 1 and not partial) else 1)
 
-    def _pack(self, weight, H, W, fwd=None, fwd_rows=0, fwd_row0=0, bwd=None, bwd_rows=0, bwd_k0=0):
-        Cout, Cin, kh, kw = weight.shape
-        check(lib().hrl_board_pack(_ptr(weight), Cout, Cin, kh, kw, H, W, _ptr(fwd), fwd_rows, fwd_row0, _ptr(bwd), bwd_rows, bwd_k0,
-                                   _stream_ptr()))
-        _count()
+    def _pack_all(self, jobs):
+        """jobs: dicts of HrlPackJob fields with tensors for the pointers -- one launch for up to MAX_BOARD_JOBS convolutions."""
+        for i in range(0, len(jobs), MAX_BOARD_JOBS):
+            chunk = jobs[i:i + MAX_BOARD_JOBS]
+            arr = (HrlPackJob * len(chunk))()
+            for j, kw in zip(arr, chunk):
+                w = kw['w']
+                j.w, (j.Cout, j.Cin, j.kh, j.kw), j.H, j.W = _ptr(w), w.shape, self.H, self.W
+                j.image_fwd, j.fwd_rows, j.fwd_row0 = _ptr(kw.get('fwd')), kw.get('fwd_rows', 0), kw.get('fwd_row0', 0)
+                j.image_bwd, j.bwd_rows, j.bwd_k0 = _ptr(kw.get('bwd')), kw.get('bwd_rows', 0), kw.get('bwd_k0', 0)
+                j.bias, j.bias_cells = _ptr(kw.get('bias')), _ptr(kw.get('bias_cells'))
+            check(lib().hrl_board_pack_many(C.byref(arr), len(chunk), _stream_ptr()))
+            _count()
 
-    def _fold(self, partials, splits, stride, grad, H, W):
-        Cout, Cin, kh, kw = grad.shape
-        check(lib().hrl_board_fold(_ptr(partials), splits, stride, _ptr(grad), Cout, Cin, kh, kw, H, W, _stream_ptr()))
-        _count()
+    def _fold_all(self):
+        """Every weight-gradient product of the backward pass onto its convolution's taps, in one launch."""
+        jobs, self.fold_jobs = self.fold_jobs, []
+        for i in range(0, len(jobs), MAX_BOARD_JOBS):
+            chunk = jobs[i:i + MAX_BOARD_JOBS]
+            arr = (HrlFoldJob * len(chunk))()
+            for j, (src, splits, stride, grad) in zip(arr, chunk):
+                j.ddense, j.splits, j.split_stride, j.dw = _ptr(src), splits, stride, _ptr(grad)
+                (j.Cout, j.Cin, j.kh, j.kw), j.H, j.W = grad.shape, self.H, self.W
+            check(lib().hrl_board_fold_many(C.byref(arr), len(chunk), _stream_ptr()))
+            _count()
 
-    def _wgrad(self, a, b, rows, cols, splits_key, grads, H, W):
-        """dense gradient (rows x cols) = A_op^T-style product over the samples, folded onto conv weights.
-        grads: list of (weight.grad tensor, first dense row)."""
-        s = self.splits[splits_key]
+    def _wgrad(self, a, b, rows, cols, region, grads):
+        """dense gradient (rows x cols) = A_op^T-style product over the samples, left as slice partials in the product's
+        workspace region; queued for the fold onto the conv weights.  grads: list of (weight.grad tensor, first dense row)."""
+        s = self.splits[region[0]]
+        ws = self.ws[self.ws_at[region]:]
         if s > 1:
-            self._gemm(a, b, None, K=self.M, N=cols, M=rows, splits=s, partial=True)
-            src, stride = self.ws, rows * cols
+            self._gemm(a, b, None, K=self.M, N=cols, M=rows, splits=s, partial=True, ws=ws)
+            stride = rows * cols
         else:
-            tmp = self.ws[:rows * cols].view(rows, cols)
-            self._gemm(a, b, tmp, K=self.M, N=cols, M=rows)
-            src, stride = self.ws, 0
+            self._gemm(a, b, ws[:rows * cols].view(rows, cols), K=self.M, N=cols, M=rows)
+            stride = 0
         for grad, row0 in grads:
-            self._fold(src[row0 * cols:], s, stride, grad, H, W)
+            self.fold_jobs.append((ws[row0 * cols:], s, stride, grad))
 
     # ------------------------------------------------------------------ forward
     def forward(self, x):
@@ -170,16 +189,16 @@ class FusedBoardNet:
         self.H, self.W = H, W
         self.x2d = x.view(M_, self.K0)
         with torch.no_grad():
-            self._pack(m.stem.weight, H, W, fwd=self.W0f, fwd_rows=D)
+            # every convolution's weights (and the biases of the stem / squeeze convolutions, one copy per cell) in one launch
+            jobs = [dict(w=m.stem.weight, fwd=self.W0f, fwd_rows=D, bias=m.stem.bias, bias_cells=self.b0)]
             for l, blk in enumerate(m.tower):
-                self._pack(blk[0].weight, H, W, fwd=self.Wf[l], fwd_rows=D, bwd=self.Wb[l], bwd_rows=D)
+                jobs.append(dict(w=blk[0].weight, fwd=self.Wf[l], fwd_rows=D, bwd=self.Wb[l], bwd_rows=D))
             heads = [(m.p_squeeze, 0), (m.v_squeeze, self.pmaps * self.cells)] + \
                 ([(m.r_squeeze, (self.pmaps + self.vmaps) * self.cells)] if self.rmaps else [])
             for sq_, row0 in heads:       # the squeeze convolutions side by side in ONE operand
-                self._pack(sq_.weight, H, W, fwd=self.Whf, fwd_rows=self.NH, fwd_row0=row0, bwd=self.Whb, bwd_rows=D, bwd_k0=row0)
-            self.b0.view(self.width, self.cells).copy_(m.stem.bias.view(-1, 1).expand(self.width, self.cells))
-            sq = [m.p_squeeze.bias, m.v_squeeze.bias] + ([m.r_squeeze.bias] if self.rmaps else [])
-            self.bh.view(-1, self.cells).copy_(torch.cat(sq).view(-1, 1).expand(-1, self.cells))
+                jobs.append(dict(w=sq_.weight, fwd=self.Whf, fwd_rows=self.NH, fwd_row0=row0, bwd=self.Whb, bwd_rows=D, bwd_k0=row0,
+                                 bias=sq_.bias, bias_cells=self.bh[row0:]))
+            self._pack_all(jobs)
             # stem: bias + ReLU in the epilogue
             self._gemm(dict(t=self.x2d), dict(t=self.W0f, packed=True), self.A0, K=self.K0, N=D, bias=self.b0, epilogue='relu')
             src = dict(t=self.A0)
@@ -224,7 +243,7 @@ class FusedBoardNet:
             heads = [(g(m.p_squeeze.weight), 0), (g(m.v_squeeze.weight), self.pmaps * self.cells)]
             if self.rmaps:
                 heads.append((g(m.r_squeeze.weight), (self.pmaps + self.vmaps) * self.cells))
-            self._wgrad(dict(t=self.dHpre, kmajor=False), dict(a_top, kmajor=False, by_row=True), self.NH, D, 'heads', heads, H, W)
+            self._wgrad(dict(t=self.dHpre, kmajor=False), dict(a_top, kmajor=False, by_row=True), self.NH, D, ('heads', 0), heads)
             self._gemm(dict(t=self.dHpre), dict(t=self.Whb, packed=True), self.dZ[L - 1], K=self.NH, N=D, epilogue='mask_stats',
                        ep=dict(y=self.Y[L - 1], scale=top['scale'], shift=top['shift'], mean=top['mean'], rstd=top['rstd']))
             for l in range(L - 1, -1, -1):
@@ -240,8 +259,8 @@ class FusedBoardNet:
                     a_in = dict(t=self.Y[l - 1], consts=(below['scale'], below['shift']), relu=True)
                 else:
                     a_in = dict(t=self.A0)
-                self._wgrad(dict(dy, kmajor=False, by_row=True), dict(a_in, kmajor=False, by_row=True), D, D, 'tower',
-                            [(g(blk[0].weight), 0)], H, W)
+                self._wgrad(dict(dy, kmajor=False, by_row=True), dict(a_in, kmajor=False, by_row=True), D, D, ('tower', l),
+                            [(g(blk[0].weight), 0)])
                 if l > 0:
                     self._gemm(dy, dict(t=self.Wb[l], packed=True), self.dZ[l - 1], K=D, N=D, epilogue='mask_stats',
                                ep=dict(y=self.Y[l - 1], scale=below['scale'], shift=below['shift'], mean=below['mean'], rstd=below['rstd']))
@@ -251,4 +270,5 @@ class FusedBoardNet:
             check(lib().hrl_bn_finalize_bwd(_ptr(self.cp), self.tiles, self.width, self.cells, M_, None, None, None, None,
                                             _ptr(g(m.stem.bias)), None, None, None, _stream_ptr()))
             _count()
-            self._wgrad(dict(t=self.dZ0, kmajor=False), dict(t=self.x2d, kmajor=False), D, self.K0, 'stem', [(g(m.stem.weight), 0)], H, W)
+            self._wgrad(dict(t=self.dZ0, kmajor=False), dict(t=self.x2d, kmajor=False), D, self.K0, ('stem', 0), [(g(m.stem.weight), 0)])
+            self._fold_all()

@@ -305,6 +305,29 @@ int32_t hrl_gemm_padded_rows(int64_t N);
 size_t hrl_board_pack_floats(int64_t rows, int64_t K);      /* floats of an image with `rows` operand rows over K */
 int hrl_board_pack(const float *w, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t H, int32_t W, float *image_fwd,
                    int32_t fwd_rows, int32_t fwd_row0, float *image_bwd, int32_t bwd_rows, int32_t bwd_k0, void *stream);
+/* Batched forms: up to HRL_MAX_BOARD_JOBS convolutions in ONE launch (a net packs all its layers' weights once per step, and
+ * folds all its weight gradients once per backward pass).  bias / bias_cells (optional, both or neither): the convolution's
+ * bias replicated per cell, bias_cells[c*H*W + q] = bias[c] -- the per-column bias of the dense product. */
+#define HRL_MAX_BOARD_JOBS 8
+typedef struct HrlPackJob {
+    const float *w;
+    int32_t Cout, Cin, kh, kw, H, W;
+    float *image_fwd;
+    int32_t fwd_rows, fwd_row0;
+    float *image_bwd;
+    int32_t bwd_rows, bwd_k0;
+    const float *bias;
+    float *bias_cells;
+} HrlPackJob;
+typedef struct HrlFoldJob {
+    const float *ddense;
+    int32_t splits;
+    int64_t split_stride;
+    float *dw;
+    int32_t Cout, Cin, kh, kw, H, W;
+} HrlFoldJob;
+int hrl_board_pack_many(const HrlPackJob *jobs, int32_t n_jobs, void *stream);
+int hrl_board_fold_many(const HrlFoldJob *jobs, int32_t n_jobs, void *stream);
 int hrl_board_fold(const float *ddense, int32_t splits, int64_t split_stride, float *dw, int32_t Cout, int32_t Cin, int32_t kh,
                    int32_t kw, int32_t H, int32_t W, void *stream);
 

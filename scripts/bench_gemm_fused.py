@@ -46,7 +46,7 @@ cases = {
     'dgrad A 2-source + mask_stats': lambda: eng._gemm(dict(t=X, t2=Y, consts=(c[0], c[1], c[2])), dict(t=W, kmajor=False), out, K=D, N=D,
                                                        epilogue='mask_stats', ep=ep_full),
     'dgrad plain + mask_stats': lambda: eng._gemm(dict(t=X), dict(t=W, kmajor=False), out, K=D, N=D, epilogue='mask_stats', ep=ep_full),
-    'wgrad plain (48 slices, partials)': lambda: eng._gemm(dict(t=X, kmajor=False), dict(t=Y, kmajor=False), None, K=M, N=D, M=D, splits=eng.splits['tower'], partial=True),
+    'wgrad plain (48 slices, partials)': lambda: eng._gemm(dict(t=X, kmajor=False), dict(t=Y, kmajor=False), None, K=M, N=D, M=D, splits=eng.splits['tower'], partial=True, ws=eng.ws),
     'wgrad both transformed': lambda: eng._gemm(dict(t=X, t2=Y, consts=(c[0], c[1], c[2]), kmajor=False, by_row=True),
                                                 dict(t=Y, consts=(c[3], c[4]), relu=True, kmajor=False, by_row=True), None, K=M, N=D, M=D,
                                                 splits=eng.splits['tower'], partial=True),
@@ -54,4 +54,4 @@ cases = {
 for k, fn in (cases.items() if __name__ == "__main__" else ()):
     print('%-40s %6.1f us' % (k, timeit(fn)))
 g = torch.empty(32, 32, 3, 3, device='cuda')
-print('%-36s %6.1f us' % ('fold (48 slices)', timeit(lambda: eng._fold(eng.ws, eng.splits['tower'], D * D, g, 3, 3))))
+print('%-36s %6.1f us' % ('fold (48 slices)', timeit(lambda: lib().hrl_board_fold(eng.ws.data_ptr(), eng.splits['tower'], D * D, g.data_ptr(), 32, 32, 3, 3, 3, 3, torch.cuda.current_stream().cuda_stream))))

@@ -14,5 +14,5 @@ for mode in (0, 1, 2):
     dbg(mode)
     for an, a in (('A plain', A0), ('A affine', A1), ('A 2-source', A2)):
         for bn, b in (('B plain', B0), ('B affine+relu', B1)):
-            print('debug %d  %-12s %-14s %6.1f us' % (mode, an, bn, timeit(lambda: eng._gemm(a, b, None, K=M, N=D, M=D, splits=sp, partial=True))))
+            print('debug %d  %-12s %-14s %6.1f us' % (mode, an, bn, timeit(lambda: eng._gemm(a, b, None, K=M, N=D, M=D, splits=sp, partial=True, ws=eng.ws))))
 dbg(0)

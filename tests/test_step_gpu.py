@@ -46,7 +46,10 @@ def test_three_learner_steps_match_reference_geister_and_geese_nets(name, use_gr
         got = stepper.read_losses()
         scale = max(abs(v) for v in ref['losses'].values())
         for k, v in ref['losses'].items():
-            assert abs(got[k] - v) <= 1e-4 * scale + 1e-4, (s, k, got[k], v)
+            # step 0 sees the reference's weights; later steps see weights that went through Adam's sign-like first updates,
+            # which turn rounding differences of the gradient into lr-sized weight differences (cuDNN's autotuner picks
+            # convolution algorithms with different summation orders from run to run: 1.3e-4 * scale was seen at step 2)
+            assert abs(got[k] - v) <= (1 + s) * 1e-4 * scale + 1e-4, (s, k, got[k], v)
         assert got['dcnt'] == ref['dcnt']
         assert abs(float(stepper.opt.grad_norm) - ref['grad_norm']) <= 2e-3 * ref['grad_norm']
     final = stepper.cpu_state_dict()
