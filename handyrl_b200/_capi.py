@@ -63,7 +63,9 @@ class HrlGemmArgs(C.Structure):
                 ('ldc', C.c_int64), ('M', C.c_int64), ('N', C.c_int64), ('K', C.c_int64),
                 ('splits', C.c_int32), ('epilogue', C.c_int32), ('workspace', C.c_void_p),
                 ('ep_y', C.c_void_p), ('ep_ldy', C.c_int64), ('ep_scale', C.c_void_p), ('ep_shift', C.c_void_p),
-                ('ep_mean', C.c_void_p), ('ep_rstd', C.c_void_p), ('col_partials', C.c_void_p)]
+                ('ep_mean', C.c_void_p), ('ep_rstd', C.c_void_p), ('col_partials', C.c_void_p),
+                ('conv_off', C.c_void_p), ('conv_mode', C.c_int32), ('conv_hw', C.c_int32), ('conv_taps', C.c_int32),
+                ('conv_cin', C.c_int32)]
 
 
 MAX_BOARD_JOBS = 8
@@ -133,6 +135,10 @@ SYMBOLS = {
     'hrl_board_pack_floats': (C.c_size_t, [C.c_int64, C.c_int64]),
     'hrl_board_pack': (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'hrl_board_expand': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
+    'hrl_conv_geometry': (C.c_int, [C.c_int32] * 5 + [C.c_void_p]),
+    'hrl_conv_pack_floats': (C.c_size_t, [C.c_int32] * 3),
+    'hrl_conv_pack': (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 3),
+    'hrl_conv_wgrad_reduce': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'hrl_board_pack_many': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'hrl_board_fold_many': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'hrl_board_fold': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),

@@ -66,7 +66,17 @@ struct GemmParams {
     const float *ep_scale, *ep_shift, *ep_mean, *ep_rstd;     // per column, may be NULL
     float *col_partials;            // [row tiles][2][N] column sums of the epilogues that produce statistics
     int debug;                      // profiling only: 1 = no MMAs, 2 = no loads/stores
+    // convolution over a board as an implicit product (no im2col in memory).  conv_off[pos * taps + tap] = (cell read by kernel
+    // tap `tap` at output cell `pos`) - pos, or kConvOutside (zero padding); wrap-around boards simply have no outside.
+    //   mode 1 (forward / input gradient): A rows are pixels of a channels-last tensor (ld = pixel stride), the reduction runs over
+    //           (tap, channel) with every tap's channels padded to whole 32-element chunks -- chunk c reads tap c / cpt.
+    //   mode 2 (weight gradient): the reduction runs over pixels, B row n is (tap, channel) = (n / cin, n % cin) of the shifted input.
+    const short *conv_off;
+    int conv_mode, conv_hw, conv_taps, conv_cin, conv_cpt;
 };
+
+constexpr short kConvOutside = -32768;
+constexpr int kConvMaxTable = 256 * 9;     // cells x taps
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -184,6 +194,27 @@ __device__ __forceinline__ float4 load_item(const Item &it, const float *base, l
     return v;
 }
 
+// weight gradient of a convolution (conv_mode 2): the item's row is (tap, channel) = (off >> 16, off & 0xFFFF), its 4 reduction
+// elements are 4 consecutive pixels; each reads the pixel's tap neighbour (or nothing outside the board)
+__device__ __forceinline__ float4 load_item_conv(const Item &it, const float *base, long long ld, int k0, int pos0, const GemmParams &p,
+                                                 const short *table) {
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (it.live()) {
+        const int ci = it.off & 0xFFFF, tap = it.off >> 16, hw = p.conv_hw;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int kk = k0 + it.k() + e;
+            if (kk >= p.K) continue;
+            int pos = pos0 + it.k() + e;
+            if (hw >= kChunkK) pos -= pos >= hw ? hw : 0;
+            else pos %= hw;
+            const short o = table[pos * p.conv_taps + tap];
+            if (o != kConvOutside) r[e] = __ldg(base + (long long)(kk + o) * ld + ci);
+        }
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+}
+
 // operand transform v = x*p[f] + y*q[f] + r[f] (relu optional) on the 4 elements of an item; elements outside the operand
 // (dead rows, reduction tail) stay exactly zero.  f = the operand row, or the reduction index k0 + k + e.
 __device__ __forceinline__ float4 transform_item(const GemmOperand &op, const Item &it, float4 x, float4 y, int k0, int k_left) {
@@ -259,6 +290,7 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
     __shared__ __align__(8) uint64_t bars[2 * kStages + 1];      // full[kStages] | empty[kStages] | accumulator done
     __shared__ uint32_t tmem_base_slot;
     __shared__ float b_consts[2][kMaxN];     // per-row constants of a single-source B transform (no registers, no per-chunk loads)
+    __shared__ short conv_off_s[kConvMaxTable];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool issuer = warp == kGemmThreads / 32;
@@ -284,6 +316,8 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
         mbar_init(smem_u32(&bars[2 * kStages]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (p.conv_mode != 0)
+        for (int i = tid; i < p.conv_hw * p.conv_taps; i += kGemmBlock) conv_off_s[i] = p.conv_off[i];
     // single-source transform with per-row constants (the weight gradient's activation operand)
     const bool b_rows = !PACKED && p.b.p != nullptr && p.b.feature_is_row && p.b.ptr2 == nullptr;
     if (b_rows) {
@@ -331,7 +365,13 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
     const uint32_t idesc = umma_idesc_tf32(kTileM, n_mma);
     Item ib[ITEMS_B];
 #pragma unroll
-    for (int u = 0; u < ITEMS_B; u++) ib[u] = make_item<B_K>(tid + u * kGemmThreads, n_pad * 8, p.b.ld, n_pad, n_here, n0);
+    for (int u = 0; u < ITEMS_B; u++) {
+        ib[u] = make_item<B_K>(tid + u * kGemmThreads, n_pad * 8, p.b.ld, n_pad, n_here, n0);
+        if (!PACKED && !B_K && p.conv_mode == 2) {          // row n -> (tap, channel)
+            const int n = ib[u].row(), tap = n / p.conv_cin;
+            ib[u].off = (n - tap * p.conv_cin) | (tap << 16);
+        }
+    }
 
     if (issuer) {
         // ---- the MMA warp: waits for a stage to be full, issues its 3 x 4 (x halves) products, commits them to the
@@ -401,15 +441,29 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
         // 32 bytes (rows 144 bytes apart: 4 wavefronts per 512-byte request, the minimum).
         constexpr int kRawLd = 36;
         float *rawA = reinterpret_cast<float *>(smem + NS * stage_bytes);
+        // (convolution: the row is a pixel, the chunk belongs to one kernel tap -> the source is the tap's neighbour pixel)
+        int conv_pos[kTileM * 8 / kGemmThreads];
+#pragma unroll
+        for (int u = 0; u < kTileM * 8 / kGemmThreads; u++)
+            conv_pos[u] = (STAGED_A && p.conv_mode == 1) ? (int)((long long)(m0 + ((tid + u * kGemmThreads) >> 3)) % p.conv_hw) : 0;
         auto issue_a = [&](int c) {
-            const int k0 = c * kChunkK, k_left = p.K - k0;
             const int st = (c - c_begin) & 1;
+            const bool conv = p.conv_mode == 1;
+            const int tap = conv ? c / p.conv_cpt : 0;
+            const int k0 = conv ? (c - tap * p.conv_cpt) * kChunkK : c * kChunkK;      // first channel / reduction index of the chunk
+            const int k_left = (conv ? p.conv_cin : p.K) - k0;
 #pragma unroll
             for (int u = 0; u < kTileM * 8 / kGemmThreads; u++) {
                 const int idx = tid + u * kGemmThreads, row = idx >> 3, j = idx & 7;
                 int bytes = row < rows_a ? (k_left - 4 * j) * 4 : 0;
                 bytes = max(0, min(16, bytes));
-                const long long off = bytes > 0 ? (long long)(m0 + row) * p.a.ld + k0 + 4 * j : 0;
+                long long src_row = m0 + row;
+                if (conv) {
+                    const short o = conv_off_s[conv_pos[u] * p.conv_taps + tap];
+                    if (o == kConvOutside) bytes = 0;
+                    src_row += o;
+                }
+                const long long off = bytes > 0 ? src_row * p.a.ld + k0 + 4 * j : 0;
                 const uint32_t dst = smem_u32(rawA + ((st * 2 + 0) * kTileM + row) * kRawLd + 4 * j);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(p.a.ptr + off), "r"(bytes) : "memory");
                 if (p.a.ptr2)
@@ -452,7 +506,9 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
             if ((p.debug & 3) != 2 && !PACKED) {
                 // all the loads first (one exposed latency per chunk, not one per item), then the transforms
 #pragma unroll
-                for (int u = 0; u < ITEMS_B; u++) vb[u] = load_item<B_K>(ib[u], Bg, p.b.ld, vec_b, adv_b, k_left);
+                for (int u = 0; u < ITEMS_B; u++)
+                    vb[u] = (!B_K && p.conv_mode == 2) ? load_item_conv(ib[u], p.b.ptr, p.b.ld, k0, k0 % p.conv_hw, p, conv_off_s)
+                                                       : load_item<B_K>(ib[u], Bg, p.b.ld, vec_b, adv_b, k_left);
                 if (b_rows) {
 #pragma unroll
                     for (int u = 0; u < ITEMS_B; u++) {
@@ -754,7 +810,24 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
     HRL_REQUIRE(g.a.ptr && g.b.ptr && (g.C || (splits > 1 && g.workspace)), HRL_ERR_BAD_ARG, "hrl_gemm_fused: NULL pointer");
     HRL_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 22) && K < (1ll << 31) && g.b.ld < (1ll << 22), HRL_ERR_BAD_ARG,
                 "hrl_gemm_fused: bad dimensions (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
-    HRL_REQUIRE(g.a.ld >= (g.a.kmajor ? K : M) && (g.b.packed || g.b.ld >= (g.b.kmajor ? K : N)) && (g.C == nullptr || g.ldc >= N),
+    HRL_REQUIRE(g.conv_mode >= 0 && g.conv_mode <= 2, HRL_ERR_BAD_ARG, "hrl_gemm_fused: conv_mode is 0, 1 or 2");
+    if (g.conv_mode != 0) {
+        HRL_REQUIRE(g.conv_off && g.conv_hw > 0 && g.conv_taps > 0 && g.conv_cin > 0 && g.conv_cin < 65536 &&
+                        (long long)g.conv_hw * g.conv_taps <= hrl::kConvMaxTable && g.a.p == nullptr && g.b.p == nullptr && g.splits >= 1,
+                    HRL_ERR_BAD_ARG, "hrl_gemm_fused: convolution geometry (at most 256 cells x 9 taps, plain operands)");
+        if (g.conv_mode == 1)
+            HRL_REQUIRE(g.b.packed && g.a.kmajor && g.a.ld >= g.conv_cin && g.a.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(g.a.ptr) & 15) == 0 &&
+                            M % g.conv_hw == 0 && K == (int64_t)g.conv_taps * ((g.conv_cin + kChunkK - 1) / kChunkK) * kChunkK && g.splits == 1,
+                        HRL_ERR_UNSUPPORTED,
+                        "hrl_gemm_fused: convolution forward needs a packed B image over taps x (channels padded to 32), 16-byte aligned "
+                        "pixel rows and whole boards");
+        else
+            HRL_REQUIRE(!g.b.packed && !g.a.kmajor && !g.b.kmajor && g.b.ld >= g.conv_cin && N == (int64_t)g.conv_taps * g.conv_cin &&
+                            K % g.conv_hw == 0,
+                        HRL_ERR_UNSUPPORTED, "hrl_gemm_fused: convolution weight gradient reduces over whole boards of pixels, N = taps x channels");
+    }
+    HRL_REQUIRE((g.conv_mode == 1 || g.a.ld >= (g.a.kmajor ? K : M)) && (g.b.packed || g.conv_mode == 2 || g.b.ld >= (g.b.kmajor ? K : N)) &&
+                    (g.C == nullptr || g.ldc >= N),
                 HRL_ERR_BAD_ARG, "hrl_gemm_fused: leading dimension smaller than the row length");
     HRL_REQUIRE(!g.a.packed && (!g.b.packed || (N <= hrl::kMaxN && g.b.p == nullptr && (reinterpret_cast<uintptr_t>(g.b.ptr) & 15) == 0)),
                 HRL_ERR_BAD_ARG, "hrl_gemm_fused: only an untransformed B operand of at most 288 rows can be a packed image");
@@ -793,13 +866,15 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
     p.ep_scale = g.ep_scale; p.ep_shift = g.ep_shift; p.ep_mean = g.ep_mean; p.ep_rstd = g.ep_rstd;
     p.col_partials = g.col_partials;
     p.debug = g_gemm_debug & 63;
+    p.conv_off = g.conv_off; p.conv_mode = g.conv_mode; p.conv_hw = g.conv_hw; p.conv_taps = g.conv_taps; p.conv_cin = g.conv_cin;
+    p.conv_cpt = (g.conv_cin + kChunkK - 1) / kChunkK;
     splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;      // no empty slices
     if (splits > 1) {
         p.C = g.workspace; p.ldc = N; p.c_split_stride = M * N;
     } else {
         p.C = g.C; p.ldc = g.ldc; p.c_split_stride = 0;
     }
-    const bool staged_a = !(g_gemm_debug & 64) && g.b.packed && g.a.kmajor && g.a.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(g.a.ptr) & 15) == 0 &&
+    const bool staged_a = (g.conv_mode == 1 || !(g_gemm_debug & 64)) && g.b.packed && g.a.kmajor && g.a.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(g.a.ptr) & 15) == 0 &&
                           (g.a.ptr2 == nullptr || (reinterpret_cast<uintptr_t>(g.a.ptr2) & 15) == 0);
     size_t smem_bytes = staged_a ? 1024 + 2 * (2 * (size_t)n_pad * kChunkK * 4) + 2 * 2 * (size_t)kTileM * 36 * 4
                                  : 1024 + (size_t)kStages * (2 * (size_t)n_pad * kChunkK * 4);

@@ -272,6 +272,73 @@ extern "C" size_t hrl_board_pack_floats(int64_t rows, int64_t K) {
     return (size_t)((K + 31) / 32) * 2 * (size_t)hrl_gemm_padded_rows(rows) * 32;
 }
 
+// ---- convolutions as implicit products (hrl_gemm_fused conv_mode 1 / 2) -----------------------------------------------
+__global__ void conv_pack_kernel(const float *__restrict__ w, int Cout, int Cin, int taps, float *__restrict__ image_fwd, int fwd_pad,
+                                 float *__restrict__ image_adj, int adj_pad) {
+    const int cin_p = (Cin + 31) / 32 * 32, cout_p = (Cout + 31) / 32 * 32;
+    const long long n = (long long)Cout * Cin * taps;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(idx % taps), ci = (int)((idx / taps) % Cin), co = (int)(idx / ((long long)taps * Cin));
+        const float v = __ldg(w + idx);
+        if (image_fwd) pack_store(image_fwd, fwd_pad, co, t * cin_p + ci, v);
+        if (image_adj) pack_store(image_adj, adj_pad, ci, (taps - 1 - t) * cout_p + co, v);      // flipped kernel, channels swapped
+    }
+}
+
+__global__ void conv_wgrad_reduce_kernel(const float *__restrict__ partials, int splits, float *__restrict__ dw, int Cout, int Cin, int taps) {
+    const long long n = (long long)Cout * Cin * taps;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(idx % taps), ci = (int)((idx / taps) % Cin), co = (int)(idx / ((long long)taps * Cin));
+        const float *src = partials + (long long)co * taps * Cin + (long long)t * Cin + ci;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        int sp = 0;
+        for (; sp + 4 <= splits; sp += 4)
+#pragma unroll
+            for (int u = 0; u < 4; u++) acc[u] += __ldg(src + (long long)(sp + u) * n);
+        for (; sp < splits; sp++) acc[0] += __ldg(src + (long long)sp * n);
+        dw[idx] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    }
+}
+
+extern "C" int hrl_conv_geometry(int32_t H, int32_t W, int32_t kh, int32_t kw, int32_t wrap, int16_t *table) {
+    HRL_REQUIRE(table && H > 0 && W > 0 && kh > 0 && kw > 0 && (kh & 1) && (kw & 1) && H * W <= 256 && kh * kw <= 9 && H * W * kh * kw <= 256 * 9,
+                HRL_ERR_BAD_ARG, "hrl_conv_geometry: odd kernels of at most 9 taps over at most 256 cells");
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++)
+            for (int a = 0; a < kh; a++)
+                for (int b = 0; b < kw; b++) {
+                    int yy = y + a - kh / 2, xx = x + b - kw / 2;
+                    int v = HRL_CONV_OUTSIDE;
+                    if (wrap) { yy = (yy % H + H) % H; xx = (xx % W + W) % W; }
+                    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = (yy * W + xx) - (y * W + x);
+                    table[(y * W + x) * kh * kw + a * kw + b] = (int16_t)v;
+                }
+    return HRL_OK;
+}
+
+extern "C" size_t hrl_conv_pack_floats(int32_t rows, int32_t channels, int32_t taps) {
+    return hrl_board_pack_floats(rows, (int64_t)taps * ((channels + 31) / 32 * 32));
+}
+
+extern "C" int hrl_conv_pack(const float *w, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, float *image_fwd, float *image_adj,
+                             void *stream) {
+    HRL_REQUIRE(w && (image_fwd || image_adj) && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && (!image_fwd || Cout <= 288) && (!image_adj || Cin <= 288),
+                HRL_ERR_BAD_ARG, "hrl_conv_pack: NULL pointer, bad shape or more than 288 operand rows");
+    const long long n = (long long)Cout * Cin * kh * kw;
+    conv_pack_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, Cout, Cin, kh * kw, image_fwd, hrl_padded_rows_dev(Cout),
+                                                                                     image_adj, hrl_padded_rows_dev(Cin));
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
+
+extern "C" int hrl_conv_wgrad_reduce(const float *partials, int32_t splits, float *dw, int32_t Cout, int32_t Cin, int32_t taps, void *stream) {
+    HRL_REQUIRE(partials && dw && splits >= 1 && Cout > 0 && Cin > 0 && taps > 0, HRL_ERR_BAD_ARG, "hrl_conv_wgrad_reduce: NULL pointer or bad shape");
+    conv_wgrad_reduce_kernel<<<grid_for((long long)Cout * Cin * taps), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partials, splits, dw, Cout,
+                                                                                                                         Cin, taps);
+    HRL_CUDA_CHECK(cudaGetLastError());
+    return HRL_OK;
+}
+
 extern "C" int hrl_board_pack_many(const HrlPackJob *jobs, int32_t n_jobs, void *stream) {
     HRL_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= HRL_MAX_BOARD_JOBS, HRL_ERR_BAD_ARG, "hrl_board_pack_many: 1..%d jobs", HRL_MAX_BOARD_JOBS);
     PackJobs pj;

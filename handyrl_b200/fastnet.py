@@ -65,6 +65,59 @@ class _SplitKLinear(torch.autograd.Function):
         return dx, dw
 
 
+# Adjoint weights of the step in flight: {(data_ptr, shape, memory format): flipped/transposed copy}.  A recurrent net calls
+# each convolution T times per step; the copy is made once.  The learner clears the cache at the start of every step
+# and ops.FlatAdam after every update (new_step): it writes the parameters from its own kernel, which no version counter sees.
+_ADJOINT = {}
+
+
+def new_step():
+    _ADJOINT.clear()
+    from . import ops
+    ops.conv_weights_changed()
+
+
+def _adjoint_weight(w, channels_last):
+    key = (w.data_ptr(), tuple(w.shape), channels_last, w._version)      # (_version: in-place updates by torch optimisers)
+    wt = _ADJOINT.get(key)
+    if wt is None:
+        wt = w.detach().transpose(0, 1).flip(2, 3)
+        wt = wt.contiguous(memory_format=torch.channels_last) if channels_last else wt.contiguous()
+        _ADJOINT[key] = wt
+    return wt
+
+
+class _ConvSame(torch.autograd.Function):
+    """Stride-1 "same" convolution whose INPUT gradient is computed as what it is -- the same kind of convolution of dy with
+    the spatially flipped, channel-transposed kernel -- i.e. by cuDNN's forward kernels.  At the shapes of the board games
+    (N = 512..16384 positions of 6x6, 64 -> 128 channels, fp32 without TF32) cuDNN's backward-data choice is
+    `dgrad2d_grouped_direct_kernel`: 803 us per call against 108 us for the forward `implicit_convolve_sgemm` of the same
+    shape -- 67% of the Geister learner step (profiles/r02_launches_cfg3_summary.txt).  Same multiply-adds, other order.
+    The weight gradient stays with cuDNN (convolution_backward, weight only)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return F.conv2d(x, w, b, padding=(w.shape[2] // 2, w.shape[3] // 2))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        pad = (w.shape[2] // 2, w.shape[3] // 2)
+        dx = dw = db = None
+        cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+        if cl:
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        if ctx.needs_input_grad[0]:
+            dx = F.conv2d(dy, _adjoint_weight(w, cl), None, padding=pad)
+        if ctx.needs_input_grad[1]:
+            dw = torch.ops.aten.convolution_backward(dy, x, w, None, (1, 1), pad, (1, 1), False, (0, 0), 1, (False, True, False))[1]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum((0, 2, 3))
+        return dx, dw, db
+
+
 class BoardConv2d(nn.Conv2d):
     """nn.Conv2d whose forward runs as a dense GEMM when the board is tiny."""
 
@@ -86,8 +139,22 @@ class BoardConv2d(nn.Conv2d):
             cache[key] = _selection(kh, kw, H, W, self.padding[0], self.padding[1], device, dtype)
         return cache[key]
 
+    def _same(self, x, wrap=False):
+        kh, kw = self.kernel_size
+        return (x.dim() == 4 and x.is_cuda and x.shape[2] * x.shape[3] <= MAX_CELLS and self.stride == (1, 1)
+                and self.dilation == (1, 1) and self.groups == 1 and self.padding_mode == ('circular' if wrap else 'zeros')
+                and kh % 2 == 1 and kw % 2 == 1 and tuple(self.padding) == (kh // 2, kw // 2) and kh * kw > 1)
+
     def forward(self, x):
         if not self._eligible(x):
+            wrap = self.padding_mode == 'circular'
+            if self._same(x, wrap):
+                from . import ops
+                if getattr(self, 'tensor_cores', True) and ops.conv_implicit_supported(x, self.weight):
+                    # tensor cores: the convolution as an implicit product over (tap, channel), no dense matrix, no im2col
+                    return ops.conv_implicit(x, self.weight, self.bias, wrap)
+                if torch.is_grad_enabled() and not wrap:
+                    return _ConvSame.apply(x, self.weight, self.bias)
             return super().forward(x)
         N, Cin, H, W = x.shape
         HW = H * W

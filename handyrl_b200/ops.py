@@ -255,6 +255,8 @@ class FlatAdam:
                                        _ptr(self.step_count), self.max_norm, self.betas[0], self.betas[1], self.eps,
                                        self.weight_decay, _ptr(self.grad_norm), s))
         _count(3)
+        from . import fastnet
+        fastnet.new_step()          # cached adjoint weights of the convolutions are stale now
 
 
 def gemm_tf32x3(a, b, bias=None, a_kmajor=True, b_kmajor=True, splits=1, out=None):
@@ -384,6 +386,126 @@ class _BoardConv(torch.autograd.Function):
 
 def board_conv(x, weight):
     return _BoardConv.apply(x, weight)
+
+
+# ---- stride-1 "same" / wrap-around convolutions as implicit tensor-core products (hrl_gemm_fused conv_mode 1 / 2) -----------
+_CONV_TABLES = {}        # (H, W, kh, kw, wrap, device) -> int16 neighbour-offset table on the device
+_CONV_IMAGES = {}        # (weight ptr, shape) -> [forward image, adjoint image, generation they were packed in]
+_CONV_GENERATION = [0]   # bumped whenever the parameters may have changed (fastnet.new_step)
+
+
+def conv_weights_changed():
+    _CONV_GENERATION[0] += 1
+
+
+def _conv_table(H, W, kh, kw, wrap, device):
+    key = (H, W, kh, kw, bool(wrap), str(device))
+    t = _CONV_TABLES.get(key)
+    if t is None:
+        import numpy as np
+        host = np.empty(H * W * kh * kw, dtype=np.int16)
+        check(lib().hrl_conv_geometry(H, W, kh, kw, int(bool(wrap)), host.ctypes.data))
+        t = _CONV_TABLES[key] = torch.from_numpy(host).to(device)
+    return t
+
+
+def _conv_images(w):
+    """The weight's packed forward / adjoint operand images, re-packed once per parameter generation."""
+    Cout, Cin, kh, kw = w.shape
+    key = (w.data_ptr(), tuple(w.shape))
+    ent = _CONV_IMAGES.get(key)
+    if ent is None:
+        z = lambda rows, ch: torch.zeros(lib().hrl_conv_pack_floats(rows, ch, kh * kw), dtype=torch.float32, device=w.device)
+        ent = _CONV_IMAGES[key] = [z(Cout, Cin), z(Cin, Cout), None]
+    gen = (_CONV_GENERATION[0], w._version)
+    if ent[2] != gen:
+        check(lib().hrl_conv_pack(_ptr(w), Cout, Cin, kh, kw, _ptr(ent[0]), _ptr(ent[1]), _stream_ptr()))
+        _count()
+        ent[2] = gen
+    return ent[0], ent[1]
+
+
+def conv_implicit_supported(x, w):
+    """Shapes the implicit products cover: fp32 CUDA, at most 256 cells and 9 taps, channel counts that are multiples of 4 (16-byte
+    pixel rows) and at most 288 (one operand tile)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and x.dim() == 4):
+        return False
+    Cout, Cin, kh, kw = w.shape
+    return (x.shape[2] * x.shape[3] <= 256 and kh * kw <= 9 and kh % 2 == 1 and kw % 2 == 1 and Cin % 4 == 0 and Cout % 4 == 0
+            and Cin <= 288 and Cout <= 288 and x.shape[1] == Cin)
+
+
+def _pixels(t):
+    """(N, C, H, W) tensor -> its channels-last (N*H*W, C) view (copying only if it is not channels-last already)."""
+    t = t.contiguous(memory_format=torch.channels_last)
+    return t, t.permute(0, 2, 3, 1).reshape(-1, t.shape[1])
+
+
+def _conv_product(pix, image, rows, cin, taps, table, hw, bias=None):
+    """out[pixel][row] = sum over (tap, channel) of pix[neighbour(pixel, tap)][channel] * image[row][tap, channel]"""
+    M = pix.shape[0]
+    out = torch.empty((M, rows), dtype=torch.float32, device=pix.device)
+    g = _capi.HrlGemmArgs()
+    g.a.ptr, g.a.ld, g.a.kmajor = _ptr(pix), pix.stride(0), 1
+    g.b.ptr, g.b.kmajor, g.b.packed = _ptr(image), 1, 1
+    g.bias, g.C, g.ldc = _ptr(bias), _ptr(out), rows
+    g.M, g.N, g.K, g.splits = M, rows, taps * ((cin + 31) // 32 * 32), 1
+    g.conv_off, g.conv_mode, g.conv_hw, g.conv_taps, g.conv_cin = _ptr(table), 1, hw, taps, cin
+    check(lib().hrl_gemm_fused(C.byref(g), _stream_ptr()))
+    _count()
+    return out
+
+
+class _ConvImplicit(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, wrap):
+        N, Cin, H, W = x.shape
+        Cout, _, kh, kw = w.shape
+        table = _conv_table(H, W, kh, kw, wrap, x.device)
+        fwd, _ = _conv_images(w)
+        xl, x2 = _pixels(x)
+        y2 = _conv_product(x2, fwd, Cout, Cin, kh * kw, table, H * W, bias=b)
+        ctx.save_for_backward(xl, w)
+        ctx.wrap, ctx.has_bias = wrap, b is not None
+        return y2.view(N, H, W, Cout).permute(0, 3, 1, 2)           # logical NCHW, channels-last in memory
+
+    @staticmethod
+    def backward(ctx, dy):
+        xl, w = ctx.saved_tensors
+        N, Cin, H, W = xl.shape
+        Cout, _, kh, kw = w.shape
+        taps = kh * kw
+        table = _conv_table(H, W, kh, kw, ctx.wrap, xl.device)
+        dyl, dy2 = _pixels(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            _, adj = _conv_images(w)
+            dx = _conv_product(dy2, adj, Cin, Cout, taps, table, H * W).view(N, H, W, Cin).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            x2 = xl.permute(0, 2, 3, 1).reshape(-1, Cin)
+            pixels, cols = x2.shape[0], taps * Cin
+            tiles = ((Cout + 127) // 128) * ((cols + 287) // 288)
+            s = lib().hrl_gemm_effective_splits(pixels, max(1, min(pixels // 64, 148 // tiles)))
+            ws = torch.empty((s, Cout, cols), dtype=torch.float32, device=xl.device)
+            g = _capi.HrlGemmArgs()
+            g.a.ptr, g.a.ld, g.a.kmajor = _ptr(dy2), Cout, 0
+            g.b.ptr, g.b.ld, g.b.kmajor = _ptr(x2), Cin, 0
+            g.C, g.ldc = (None if s > 1 else _ptr(ws)), cols
+            g.M, g.N, g.K, g.splits, g.workspace = Cout, cols, pixels, s, (_ptr(ws) if s > 1 else None)
+            g.conv_off, g.conv_mode, g.conv_hw, g.conv_taps, g.conv_cin = _ptr(table), 2, H * W, taps, Cin
+            check(lib().hrl_gemm_fused(C.byref(g), _stream_ptr()))
+            dw = torch.empty_like(w, memory_format=torch.contiguous_format)
+            check(lib().hrl_conv_wgrad_reduce(_ptr(ws), s, _ptr(dw), Cout, Cin, taps, _stream_ptr()))
+            _count(2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.sum(0)
+        return dx, dw, db, None
+
+
+def conv_implicit(x, w, b=None, wrap=False):
+    """Stride-1 convolution with `same` zero padding (wrap=False) or wrap-around padding on both axes (wrap=True) of a board of at most
+    256 cells, forward / input gradient / weight gradient on the tensor cores at fp32-class accuracy (3xTF32)."""
+    return _ConvImplicit.apply(x, w, b, bool(wrap))
 
 
 class _LstmGates(torch.autograd.Function):

@@ -434,6 +434,7 @@ class LearnerStep:
 
     # -- the device work of one step, on the current stream (inputs already in self.dev)
     def _part_forward(self):
+        fastnet.new_step()          # adjoint-weight copies of the previous step are stale: the optimiser has run
         self.opt.zero_grad()
         if self.engine is not None:
             B, T, P, Pa, A = self.dims

@@ -247,7 +247,27 @@ typedef struct HrlGemmArgs {
     const float *ep_scale, *ep_shift;   /* per column; NULL = 1 / 0                                    */
     const float *ep_mean, *ep_rstd;     /* per column; NULL = second sum is sum(C * y)                 */
     float *col_partials;         /* [ceil(M/128)][2][N] floats, or NULL                                */
+    /* Convolution over a board as an implicit product (replaces cuDNN's fp32 SIMT kernels for the stride-1 "same" / wrap-around
+     * convolutions of the board nets: reference geister.py:18-56 ConvLSTM cells, hungry_geese.py:20-37 TorusConv2d).  Activations
+     * are channels-last: a row is a pixel, ld its stride in floats.  conv_off[cell * taps + tap] = (cell the tap reads) - cell, or
+     * HRL_CONV_OUTSIDE under zero padding; wrap-around boards have no outside (hrl_conv_geometry fills it).
+     *   conv_mode 1  forward / input gradient: A = input pixels (M = pixels, a.ld >= conv_cin), B = hrl_conv_pack image, K = taps *
+     *                (conv_cin padded to a multiple of 32); the input gradient is the same product of dy with the adjoint image.
+     *   conv_mode 2  weight gradient: A = dy [pixels][Cout] (kmajor 0), B = input [pixels][conv_cin] (kmajor 0), N = taps * conv_cin,
+     *                K = pixels, split over K slices; hrl_conv_wgrad_reduce sums the slices into the (Cout, Cin, kh, kw) gradient. */
+    const int16_t *conv_off;
+    int32_t conv_mode, conv_hw, conv_taps, conv_cin;
 } HrlGemmArgs;
+
+#define HRL_CONV_OUTSIDE (-32768)
+/* table (H*W*kh*kw int16, host memory) of the neighbour offsets above; wrap != 0: the board is a torus */
+int hrl_conv_geometry(int32_t H, int32_t W, int32_t kh, int32_t kw, int32_t wrap, int16_t *table);
+/* weights (Cout, Cin, kh, kw) -> packed B images (zero them once): forward (rows = Cout, reduction = tap-major, Cin padded to 32)
+ * and adjoint (rows = Cin, reduction = flipped tap, Cout padded to 32).  Either may be NULL. */
+size_t hrl_conv_pack_floats(int32_t rows, int32_t channels, int32_t taps);
+int hrl_conv_pack(const float *w, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, float *image_fwd, float *image_adj, void *stream);
+/* dw[co][ci][a][b] = sum over slices of partials[s][co][(a*kw+b)*Cin + ci]  (fixed order) */
+int hrl_conv_wgrad_reduce(const float *partials, int32_t splits, float *dw, int32_t Cout, int32_t Cin, int32_t taps, void *stream);
 
 int hrl_gemm_fused(const HrlGemmArgs *args, void *stream);
 

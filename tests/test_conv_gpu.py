@@ -1,0 +1,77 @@
+"""Convolutions over a board as implicit tensor-core products (ops.conv_implicit: hrl_gemm_fused conv_mode 1 / 2, hrl_conv_pack,
+hrl_conv_wgrad_reduce) against float64 F.conv2d: zero `same` padding (Geister's ConvLSTM cells, reference geister.py:18-56) and
+wrap-around padding (Hungry Geese's TorusConv2d, reference hungry_geese.py:20-37); output, input gradient, weight and bias gradient."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # N, Cin, Cout, H, W, kh, kw, wrap, bias
+    (37, 64, 128, 6, 6, 3, 3, False, True),       # Geister ConvLSTM gates: [x, h] 64 maps -> 4 x 32 gate maps
+    (21, 32, 32, 7, 11, 3, 3, True, True),        # Hungry Geese torus block
+    (9, 36, 20, 6, 6, 3, 3, False, False),        # channel counts that are not multiples of 32: padded chunks
+    (130, 8, 12, 3, 3, 3, 3, False, True),        # fewer cells (9) than a chunk has elements
+    (5, 16, 288, 5, 4, 1, 3, True, False),        # one-row kernel, widest operand tile
+    (3, 288, 8, 4, 4, 3, 1, False, True),
+]
+
+
+@pytest.mark.parametrize('N,Cin,Cout,H,W,kh,kw,wrap,bias', CASES)
+@pytest.mark.parametrize('channels_last', [True, False])
+def test_conv_implicit_matches_float64(N, Cin, Cout, H, W, kh, kw, wrap, bias, channels_last):
+    from handyrl_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(N * 1000 + Cin)
+    x = torch.randn(N, Cin, H, W, device='cuda', generator=g)
+    w = torch.randn(Cout, Cin, kh, kw, device='cuda', generator=g) * 0.2
+    b = torch.randn(Cout, device='cuda', generator=g) if bias else None
+    dy = torch.randn(N, Cout, H, W, device='cuda', generator=g)
+    if channels_last:
+        x, dy = x.contiguous(memory_format=torch.channels_last), dy.contiguous(memory_format=torch.channels_last)
+    assert ops.conv_implicit_supported(x, w)
+    xs, ws = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    bs = b.clone().requires_grad_(True) if bias else None
+    ops.conv_weights_changed()
+    y = ops.conv_implicit(xs, ws, bs, wrap)
+    y.backward(dy)
+
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True) if bias else None
+    if wrap:
+        xp = F.pad(xd, (kw // 2, kw // 2, kh // 2, kh // 2), mode='circular')
+        yd = F.conv2d(xp, wd, bd)
+    else:
+        yd = F.conv2d(xd, wd, bd, padding=(kh // 2, kw // 2))
+    yd.backward(dy.double())
+
+    def close(got, want, what, tol=3e-6, red=Cin * kh * kw):
+        # 3xTF32 products: ~1e-6 of sum |a||b|; the bound below is in units of the result's largest magnitude
+        scale = want.abs().max().item() + 1e-12
+        err = (got.double() - want).abs().max().item()
+        assert err <= tol * scale * (1 + red ** 0.5 / 8), (what, err, scale)
+
+    assert y.shape == yd.shape
+    close(y, yd, 'output')
+    close(xs.grad, xd.grad, 'input gradient', red=Cout * kh * kw)
+    close(ws.grad, wd.grad, 'weight gradient', red=N * H * W)
+    if bias:
+        close(bs.grad, bd.grad, 'bias gradient', tol=1e-5, red=1)
+
+
+def test_rewritten_modules_use_the_implicit_products():
+    """fastnet routes nn.Conv2d (zeros / circular `same` padding) over boards too large for the dense form to conv_implicit."""
+    from handyrl_b200 import fastnet, ops
+    torch.manual_seed(0)
+    for mode in ('zeros', 'circular'):
+        conv = torch.nn.Conv2d(16, 24, 3, padding=1, padding_mode=mode).cuda()
+        ref = torch.nn.Conv2d(16, 24, 3, padding=1, padding_mode=mode).cuda().double()
+        ref.load_state_dict({k: v.double() for k, v in conv.state_dict().items()})
+        net = torch.nn.Sequential(conv)
+        assert fastnet.optimize_small_boards(net) == 1
+        x = torch.randn(11, 16, 6, 6, device='cuda')
+        before = ops.LAUNCHES['n']
+        fastnet.new_step()
+        y = net(x)
+        assert ops.LAUNCHES['n'] > before
+        assert (y.double() - ref(x.double())).abs().max().item() < 1e-4
