@@ -256,19 +256,22 @@ def loss_kernel_name(A):
     return 'hrl::loss_group_kernel' if A <= 32 else ('hrl::loss_bulk_kernel' if (A > 256 and A % 4 == 0) else 'hrl::loss_rows_kernel')
 
 
-def time_loss_alone(B, T, P, A, turn_based, observation, args, device, reps):
+def time_loss_alone(B, T, P, A, turn_based, observation, args, device, reps, bf16=False):
     """Average device time (ms) of hrl_loss_fwd_bwd launched back to back over input sets that together exceed L2."""
     from handyrl_b200 import ops
     from handyrl_b200.synthetic import synthetic_batch, synthetic_outputs, bytes_per_cell
     Pa = 1 if (turn_based and not observation) else P
-    per_set = bytes_per_cell(P, Pa, A, T, 0) * B * T
+    per_set = (bytes_per_cell(P, Pa, A, T, 0) - (4 * Pa * A if bf16 else 0)) * B * T     # bf16 logits + gradients: 8 not 12 bytes / action
     n = max(2, min(64, int(2 * L2_BYTES / per_set) + 1))
     sets = []
     for i in range(n):
         b = synthetic_batch(B, T, P, A, turn_based=turn_based, observation=observation, seed=300 + i, with_obs=False)
         o = synthetic_outputs(b, seed=400 + i)
-        sets.append(({k: v.to(device) for k, v in o.items()}, {k: v.to(device) for k, v in b.items()},
-                     ops.LossBuffers(B, T, P, Pa, A, True, False, device)))
+        o = {k: v.to(device) for k, v in o.items()}
+        if bf16:
+            o['policy'] = o['policy'].to(torch.bfloat16)
+        sets.append((o, {k: v.to(device) for k, v in b.items()},
+                     ops.LossBuffers(B, T, P, Pa, A, True, False, device, policy_dtype=o['policy'].dtype)))
     for o, b, buf in sets:
         ops.loss_fwd_bwd(o, b, args, buffers=buf)
     torch.cuda.synchronize()
@@ -481,13 +484,15 @@ def b200_arm(opt, w):
 
     # ---- the loss kernel alone on cold inputs (distinct input sets larger than L2), at the bench shape and at the
     #      wide-row shape of configs[4]'s per-GPU shard (where an HBM roofline is physically meaningful); K2 alone
-    alone, wide, k2 = None, None, None
+    alone, wide, wide16, k2 = None, None, None, None
     if rank == 0 and not opt.quick:
         alone = time_loss_alone(B, T, P, A, w['turn_based'], w['observation'], args, device, reps=200)
         if not opt.no_wide:
             ww = WORKLOADS['cfg5shard']
             wide = time_loss_alone(ww['B'], ww['T'], ww['P'], ww['A'], ww['turn_based'], ww['observation'], train_args(ww),
                                    device, reps=40)
+            wide16 = time_loss_alone(ww['B'], ww['T'], ww['P'], ww['A'], ww['turn_based'], ww['observation'], train_args(ww),
+                                     device, reps=40, bf16=True)
             k2 = {'cfg5shard': time_gather_alone(ww, device, reps=5)}
             if w['obs_shape'] is not None and opt.workload != 'cfg5shard':
                 k2[opt.workload] = time_gather_alone(w, device, reps=20)
@@ -545,6 +550,13 @@ def b200_arm(opt, w):
             'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
             'kernel': loss_kernel_name(WORKLOADS['cfg5shard']['A']) + ' (hrl_loss_fwd_bwd)', 'kernel_us': wide['ms'] * 1e3,
             'algorithmic_bytes': wide['bytes'], 'traffic': None if traffic_all is None else traffic_all.get('cfg5shard')}
+    if wide16 is not None:
+        gbs = wide16['bytes'] / (wide16['ms'] * 1e-3) / 1e9
+        line['roofline_wide_rows_bf16'] = {
+            'workload': 'the same shape with HrlLossArgs.io_bf16: logits read and policy gradient written as bf16 (8 instead of 12 bytes '
+                        'per action), all arithmetic fp32 (tests/test_loss_gpu.py: losses bit-identical to the fp32 pass)',
+            'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak, 'kernel_us': wide16['ms'] * 1e3,
+            'algorithmic_bytes': wide16['bytes'], 'speedup_vs_fp32_io': None if wide is None else wide['ms'] / wide16['ms']}
     if k2:
         line['roofline_k2'] = {
             name: {'bound': 'hbm', 'kernel': 'hrl::gather_pad_kernel (hrl_gather_pad)', 'achieved': r['bytes'] / (r['ms'] * 1e-3) / 1e9,

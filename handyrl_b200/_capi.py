@@ -46,7 +46,7 @@ class HrlLossArgs(C.Structure):
         ('tap_target_value', C.c_void_p), ('tap_target_return', C.c_void_p), ('tap_advantage', C.c_void_p),
         ('tap_logp', C.c_void_p), ('tap_rho', C.c_void_p), ('tap_entropy', C.c_void_p),
         ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
-        ('tuning', HrlLossTuning),
+        ('tuning', HrlLossTuning), ('io_bf16', C.c_int32),
     ]
 
 

@@ -28,6 +28,8 @@
 // Phases: (0) stage  (1) per-row softmax statistics  (2a-2c) targets / recurrences / per-cell terms
 //         (publish six block partials; the last CTA folds them in a fixed order in fp64)
 //         (3) gradients.
+#include <cuda_bf16.h>
+
 #include "loss_common.cuh"
 #include <stdlib.h>
 
@@ -570,12 +572,24 @@ __global__ void __launch_bounds__(544, 2) loss_bulk_kernel(const LossParams prm)
     // small per-cell tensors first (a few KB, cp.async) so that they do not queue behind the bulk traffic
     stage_small(prm, L, smem, c);
     __syncthreads();
+    // io_bf16: logits arrive (and gradients leave) as bf16 -- 8 bytes per action instead of 12 over the whole pass.  A raw row is
+    // loaded into the UPPER half of its fp32 slot (one bulk load per row), widened in place by the statistics pass, and the
+    // gradient row is narrowed into the LOWER half before its bulk store: no extra shared memory, no cross-row hazards.
+    const bool io16 = a.io_bf16 != 0;
     if (tid == 0) {
         for (int ch = 0; ch < nchunk; ch++) {
             const int rows = min(NC, R - ch * NC);
-            const uint32_t bytes = (uint32_t)rows * A * 4;
-            mbar_expect_tx(raw_full + ch, bytes);
-            bulk_load(smem + L.z + (size_t)ch * NC * A, a.policy_raw + ep_off + (size_t)ch * NC * A, bytes, raw_full + ch);
+            if (!io16) {
+                const uint32_t bytes = (uint32_t)rows * A * 4;
+                mbar_expect_tx(raw_full + ch, bytes);
+                bulk_load(smem + L.z + (size_t)ch * NC * A, a.policy_raw + ep_off + (size_t)ch * NC * A, bytes, raw_full + ch);
+            } else {
+                mbar_expect_tx(raw_full + ch, (uint32_t)rows * A * 2);
+                const uint16_t *src = reinterpret_cast<const uint16_t *>(a.policy_raw) + ep_off + (size_t)ch * NC * A;
+                for (int r = 0; r < rows; r++)
+                    bulk_load(reinterpret_cast<uint16_t *>(smem + L.z + (size_t)(ch * NC + r) * A) + A, src + (size_t)r * A, (uint32_t)A * 2,
+                              raw_full + ch);
+            }
         }
     }
     // action mask of this warp's first row -> registers (overlaps the wait for the staged tensors)
@@ -625,7 +639,14 @@ __global__ void __launch_bounds__(544, 2) loss_bulk_kernel(const LossParams prm)
         for (int k4 = 0; k4 < 4; k4++) {
             const int j = (k4 * 32 + lane) * 4;
             const bool ok = j < A;
-            const float4 x = *reinterpret_cast<const float4 *>(zrow + (ok ? j : 0));
+            float4 x;
+            if (!io16) {
+                x = *reinterpret_cast<const float4 *>(zrow + (ok ? j : 0));
+            } else {             // four bf16 of the raw row in the slot's upper half: a bf16 is the top half of the fp32
+                const uint2 h = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(zrow) + A + (ok ? j : 0));
+                x = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xFFFF0000u), __uint_as_float(h.y << 16),
+                                __uint_as_float(h.y & 0xFFFF0000u));
+            }
             z4[k4].x = ok ? fmaf(x.x, scale, -am4[k4].x) : -INFINITY;  // train.py:178-181
             z4[k4].y = ok ? fmaf(x.y, scale, -am4[k4].y) : -INFINITY;
             z4[k4].z = ok ? fmaf(x.z, scale, -am4[k4].z) : -INFINITY;
@@ -713,20 +734,36 @@ __global__ void __launch_bounds__(544, 2) loss_bulk_kernel(const LossParams prm)
                     const float pj = fast_exp2(lp * kLog2e);
                     g[cc] = pj * fmaf(lp, sk, swk);
                 }
+                if (io16) {          // the action's own term goes in before the row is narrowed
+#pragma unroll
+                    for (int cc = 0; cc < 4; cc++)
+                        if (j + cc == act) g[cc] -= scale * f.w;
+                }
                 o4[k4] = make_float4(g[0], g[1], g[2], g[3]);
             }
+            if (io16) __syncwarp();      // the narrowed row overlays OTHER lanes' fp32 elements: every lane has read first
 #pragma unroll
             for (int k4 = 0; k4 < 4; k4++) {
                 const int j = (k4 * 32 + lane) * 4;
-                if (j < A) *reinterpret_cast<float4 *>(zrow + j) = o4[k4];
+                if (j >= A) continue;
+                if (!io16) {
+                    *reinterpret_cast<float4 *>(zrow + j) = o4[k4];
+                } else {
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(o4[k4].x, o4[k4].y), hi = __floats2bfloat162_rn(o4[k4].z, o4[k4].w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+                    pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+                    *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(zrow) + j) = pk;
+                }
             }
         }
         __syncwarp();
-        if (lane == 0 && scale != 0.0f) zrow[act] -= scale * f.w;
+        if (lane == 0 && scale != 0.0f && !io16) zrow[act] -= scale * f.w;
         fence_proxy_async();   // generic-proxy writes -> visible to the bulk-copy engine
         __syncwarp();
         if (lane == 0) {
-            bulk_store(a.dpolicy_raw + grow * A, zrow, (uint32_t)A * 4);
+            if (io16) bulk_store(reinterpret_cast<uint16_t *>(a.dpolicy_raw) + grow * A, zrow, (uint32_t)A * 2);
+            else bulk_store(a.dpolicy_raw + grow * A, zrow, (uint32_t)A * 4);
             if (prm.has_v) a.dvalue_raw[grow] = f.gv;
             if (prm.has_r) a.dreturn_raw[grow] = f.gr;
         }
@@ -827,7 +864,7 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
     const int mode = tune.variant - 1;               // -1 auto, 0 direct, 1 staged I/O, 2 bulk, 3 element, 4 group
 
     // ---- bulk (TMA) kernel: wide rows
-    if (LPR == 32 && a.A <= 512 && a.A % 4 == 0 && aligned16 && (mode == -1 || mode == 2)) {
+    if (LPR == 32 && a.A <= 512 && a.A % (a.io_bf16 ? 8 : 4) == 0 && aligned16 && (mode == -1 || mode == 2 || a.io_bf16)) {
         const size_t two_per_sm = 112 * 1024;     // dynamic shared memory that still lets two CTAs share an SM
         const int force_cs = tune.cluster;
         int NCmax = tune.consumers ? tune.consumers : 16;
@@ -866,6 +903,9 @@ extern "C" int hrl_loss_fwd_bwd(const HrlLossArgs *args, void *stream_) {
         }
         HRL_REQUIRE(mode != 2, HRL_ERR_UNSUPPORTED, "hrl_loss_fwd_bwd: bulk kernel forced but the window does not fit");
     }
+    HRL_REQUIRE(!a.io_bf16, HRL_ERR_UNSUPPORTED,
+                "hrl_loss_fwd_bwd: bf16 logits / gradients are built for the wide-row (bulk) kernel only: 256 < A <= 512, A %% 8 == 0, "
+                "16-byte aligned tensors, a window that fits in shared memory (A=%d T=%d)", a.A, a.T);
 
     // ---- group kernel: small action spaces, RL = 2^k >= A lanes per row (default for A <= 32)
     if (a.A <= 32 && (mode == -1 || mode == 4)) {

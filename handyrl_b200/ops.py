@@ -53,10 +53,10 @@ def algo_id(name):
 class LossBuffers:
     """Pre-allocated outputs of one fused loss launch (re-used across steps / graph replays)."""
 
-    def __init__(self, B, T, P, Pa, A, has_value, has_return, device, taps=False):
+    def __init__(self, B, T, P, Pa, A, has_value, has_return, device, taps=False, policy_dtype=torch.float32):
         f = dict(dtype=torch.float32, device=device)
         self.dims = (B, T, P, Pa, A)
-        self.dpolicy = torch.empty((B, T, Pa, A), **f)
+        self.dpolicy = torch.empty((B, T, Pa, A), dtype=policy_dtype, device=device)      # bf16 logits get bf16 gradients
         self.dvalue = torch.empty((B, T, Pa, 1), **f) if has_value else None
         self.dreturn = torch.empty((B, T, Pa, 1), **f) if has_return else None
         self.losses = torch.zeros(NUM_LOSS, **f)
@@ -82,14 +82,20 @@ def loss_fwd_bwd(outputs, batch, args, buffers=None, taps=False, tuning=None):
              cluster, consumers, threads, unstaged, trace (an int64 CUDA tensor of >= 32 elements)
     returns  LossBuffers with .losses = [p, v, r, ent, total, dcnt] and the gradients.
     """
-    policy = _dev_f32(outputs['policy'], 'policy')
+    policy = outputs['policy']
+    io_bf16 = policy.dtype == torch.bfloat16       # wide rows only: 8 instead of 12 bytes per action through HBM (include/hrl_b200.h)
+    if io_bf16:
+        if not (policy.is_cuda and policy.is_contiguous()):
+            raise _capi.HrlError('handyrl_b200: bf16 policy logits must be a contiguous CUDA tensor')
+    else:
+        policy = _dev_f32(policy, 'policy')
     B, T, Pa, A = policy.shape
     P = batch['turn_mask'].shape[2]
     value = _dev_f32(outputs.get('value'), 'value')
     ret_head = _dev_f32(outputs.get('return'), 'return')
     if buffers is None:
-        buffers = LossBuffers(B, T, P, Pa, A, value is not None, ret_head is not None, policy.device, taps=taps)
-    assert buffers.dims == (B, T, P, Pa, A)
+        buffers = LossBuffers(B, T, P, Pa, A, value is not None, ret_head is not None, policy.device, taps=taps, policy_dtype=policy.dtype)
+    assert buffers.dims == (B, T, P, Pa, A) and buffers.dpolicy.dtype == policy.dtype
 
     # static buffers (CUDA-graph replays): the argument block of the previous call is still valid
     key = (policy.data_ptr(), 0 if value is None else value.data_ptr(), 0 if ret_head is None else ret_head.data_ptr(),
@@ -132,6 +138,7 @@ def loss_fwd_bwd(outputs, batch, args, buffers=None, taps=False, tuning=None):
         t = buffers.taps
         a.tap_target_value, a.tap_target_return, a.tap_advantage = _ptr(t['target_value']), _ptr(t['target_return']), _ptr(t['advantage'])
         a.tap_logp, a.tap_rho, a.tap_entropy = _ptr(t['logp']), _ptr(t['rho']), _ptr(t['entropy'])
+    a.io_bf16 = int(io_bf16)
     a.workspace = _ptr(buffers.workspace)
     a.workspace_bytes = buffers.workspace.numel()
     if tuning:

@@ -125,6 +125,10 @@ typedef struct HrlLossArgs {
                                     left zero by every call                                  */
     size_t workspace_bytes;
     HrlLossTuning tuning;        /* zero-initialise for the defaults                         */
+    int32_t io_bf16;             /* 1: policy_raw and dpolicy_raw hold bf16 (same shapes): 8 instead of 12 bytes per action
+                                    move through HBM.  Wide rows only (256 < A <= 512, A % 8 == 0); everything in between --
+                                    masks, softmax statistics, targets, the gradient before its final rounding -- stays fp32, so
+                                    the losses equal those of the fp32 call on the widened logits bit for bit              */
 } HrlLossArgs;
 
 /* Bytes of workspace hrl_loss_fwd_bwd needs for these dimensions (host call, no GPU work). */

@@ -247,3 +247,34 @@ def test_action_space_beyond_the_built_range_is_refused():
     outs = synthetic_outputs(batch, seed=2)
     with pytest.raises(_capi.HrlError, match='not built'):
         ops.loss_fwd_bwd({k: v.cuda() for k, v in outs.items()}, {k: v.cuda() for k, v in batch.items()}, args)
+
+
+@pytest.mark.parametrize('B,T,P,A,turn_based,cluster', [(64, 64, 2, 512, True, 0), (33, 20, 2, 320, True, 1), (16, 32, 4, 264, False, 2)])
+def test_bf16_logit_io_equals_the_fp32_pass_on_the_same_logits(B, T, P, A, turn_based, cluster):
+    """HrlLossArgs.io_bf16 (wide rows): the logits are read and the policy gradient is written as bf16, everything in between is
+    the fp32 arithmetic of the default path.  So against the fp32 call on the SAME (bf16-representable) logits: the six losses
+    and the value gradient are bit-identical, and the policy gradient is the fp32 one rounded to nearest-even bf16 -- tolerance
+    of the flag: half a bf16 ulp (2^-9 relative) of each gradient element, nothing else."""
+    from handyrl_b200 import ops
+    from handyrl_b200.synthetic import synthetic_batch, synthetic_outputs
+    args = {'turn_based_training': turn_based, 'observation': False, 'gamma': 0.8, 'lambda': 0.7, 'burn_in_steps': 0,
+            'entropy_regularization': 0.1, 'entropy_regularization_decay': 0.1, 'policy_target': 'UPGO', 'value_target': 'VTRACE'}
+    batch = synthetic_batch(B, T, P, A, turn_based=turn_based, seed=5, with_obs=False)
+    outs = synthetic_outputs(batch, seed=6)
+    db, do = {k: v.cuda() for k, v in batch.items()}, {k: v.cuda() for k, v in outs.items()}
+    half = dict(do, policy=do['policy'].to(torch.bfloat16))
+    widened = dict(do, policy=half['policy'].float())
+    tuning = {'variant': 'bulk', 'cluster': cluster} if cluster else {'variant': 'bulk'}
+    ref = ops.loss_fwd_bwd(widened, db, args, tuning=tuning)
+    res = ops.loss_fwd_bwd(half, db, args, tuning=tuning)
+    torch.cuda.synchronize()
+    assert res.dpolicy.dtype == torch.bfloat16
+    assert torch.equal(res.losses, ref.losses)
+    assert torch.equal(res.dvalue, ref.dvalue)
+    assert torch.equal(res.dpolicy, ref.dpolicy.to(torch.bfloat16))
+    # and the flag refuses shapes the wide-row kernel does not cover instead of silently widening
+    small = synthetic_batch(8, 8, 2, 9, seed=1, with_obs=False)
+    so = synthetic_outputs(small, seed=2)
+    with pytest.raises(Exception, match='bf16'):
+        ops.loss_fwd_bwd(dict({k: v.cuda() for k, v in so.items()}, policy=so['policy'].cuda().to(torch.bfloat16)),
+                         {k: v.cuda() for k, v in small.items()}, args)
