@@ -294,6 +294,51 @@ def time_loss_alone(B, T, P, A, turn_based, observation, args, device, reps, bf1
     return {'ms': e0.elapsed_time(e1) / (rounds * n), 'bytes': per_set, 'sets': n}
 
 
+def time_tower_products(engine, device):
+    """The three tcgen05 3xTF32 products of one layer of the fused tower engine (handyrl_b200/tower.py), each alone: 20 launches
+    captured in a CUDA graph, replayed 5 times.  flops = 2 M N K of the fp32 product the kernel computes (the hardware executes three
+    TF32 instructions per product at half the bf16 rate, i.e. a ceiling of 1/6 of the bf16 peak)."""
+    M, D = engine.M, engine.D
+    f = dict(dtype=torch.float32, device=device)
+    X, Y, out = torch.randn(M, D, **f), torch.randn(M, D, **f), torch.empty(M, D, **f)
+    c = [torch.rand(D, **f) for _ in range(5)]
+    sp = engine.splits['tower']
+    ws = engine.ws
+    cases = {
+        'forward (A = relu(bn(y)) on the fly, packed weights, BN-statistics epilogue)':
+            lambda: engine._gemm(dict(t=X, consts=(c[0], c[1]), relu=True), dict(t=engine.Wf[0], packed=True), out, K=D, N=D, epilogue='stats'),
+        'input gradient (A = BN backward of two sources on the fly, ReLU-mask + BN-sums epilogue)':
+            lambda: engine._gemm(dict(t=X, t2=Y, consts=(c[0], c[1], c[2])), dict(t=engine.Wb[0], packed=True), out, K=D, N=D,
+                                 epilogue='mask_stats', ep=dict(y=Y, scale=c[0], shift=c[1], mean=c[2], rstd=c[3])),
+        'weight gradient (both operands transformed, %d K slices)' % sp:
+            lambda: engine._gemm(dict(t=X, t2=Y, consts=(c[0], c[1], c[2]), kmajor=False, by_row=True),
+                                 dict(t=Y, consts=(c[3], c[4]), relu=True, kmajor=False, by_row=True), None, K=M, N=D, M=D, splits=sp,
+                                 partial=True, ws=ws),
+    }
+    res = {}
+    side = torch.cuda.Stream(device=device)
+    for name, fn in cases.items():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(20):
+                    fn()
+            graph.replay()
+            side.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            for _ in range(5):
+                graph.replay()
+            e1.record(side)
+            side.synchronize()
+        us = e0.elapsed_time(e1) / 100 * 1e3
+        res[name] = {'kernel_us': us, 'flops': 2.0 * M * D * D, 'achieved': 2.0 * M * D * D / (us * 1e-6) / 1e12}
+    return res
+
+
 def time_gather_alone(w, device, reps=20):
     """The replay gather/pad kernel (K2) alone: episodes of the workload's shape resident in the device ring, B windows per
     launch into distinct output batches that together exceed L2.  Algorithmic bytes = batch bytes written + stored rows read
@@ -484,9 +529,11 @@ def b200_arm(opt, w):
 
     # ---- the loss kernel alone on cold inputs (distinct input sets larger than L2), at the bench shape and at the
     #      wide-row shape of configs[4]'s per-GPU shard (where an HBM roofline is physically meaningful); K2 alone
-    alone, wide, wide16, k2 = None, None, None, None
+    alone, wide, wide16, k2, gemm = None, None, None, None, None
     if rank == 0 and not opt.quick:
         alone = time_loss_alone(B, T, P, A, w['turn_based'], w['observation'], args, device, reps=200)
+        if stepper.engine is not None:
+            gemm = time_tower_products(stepper.engine, device)
         if not opt.no_wide:
             ww = WORKLOADS['cfg5shard']
             wide = time_loss_alone(ww['B'], ww['T'], ww['P'], ww['A'], ww['turn_based'], ww['observation'], train_args(ww),
@@ -557,6 +604,18 @@ def b200_arm(opt, w):
                         'per action), all arithmetic fp32 (tests/test_loss_gpu.py: losses bit-identical to the fp32 pass)',
             'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak, 'kernel_us': wide16['ms'] * 1e3,
             'algorithmic_bytes': wide16['bytes'], 'speedup_vs_fp32_io': None if wide is None else wide['ms'] / wide16['ms']}
+    if gemm is not None:
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                tpeak, tsrc = float(json.load(f)['bf16_tflops']), 'measured (MEASURED_PEAKS.json bf16_tflops, burst)'
+        except Exception:
+            tpeak, tsrc = 2250.0, 'fallback (nominal dense bf16)'
+        line['roofline_net_gemm'] = {
+            'kernel': 'hrl::gemm_tf32x3_kernel (hrl_gemm_fused): the net of this workload, 14 launches / ~75% of the step', 'bound': 'tensor',
+            'unit': 'TFLOP/s', 'peak': tpeak, 'peak_source': tsrc,
+            'note': 'M x 288 x 288 products of one tower layer, alone; fp32-class accuracy = 3 TF32 tensor instructions per product at half '
+                    'the bf16 rate: ceiling peak/6; a single 128-row tile per CTA (prologue/epilogue not overlapped)',
+            'products': {k: dict(v, frac=v['achieved'] / tpeak, frac_of_3xtf32_ceiling=v['achieved'] / (tpeak / 6)) for k, v in gemm.items()}}
     if k2:
         line['roofline_k2'] = {
             name: {'bound': 'hbm', 'kernel': 'hrl::gather_pad_kernel (hrl_gather_pad)', 'achieved': r['bytes'] / (r['ms'] * 1e-3) / 1e9,
