@@ -100,16 +100,44 @@ __global__ void board_fold_kernel(const FoldJobs jobs) {
     const int i_per = (Cin + n_groups - 1) / n_groups, i_lo = gy * i_per, i_hi = min(Cin, i_lo + i_per);
     const int c_lo = i_lo * HW, c_n = (i_hi - i_lo) * HW;          // this CTA's column range
     const float *base = ddense + (long long)o * n;
-    for (int e0 = threadIdx.x; e0 < HW * c_n; e0 += blockDim.x) {
-        const int e = (e0 / c_n) * cols + c_lo + e0 % c_n;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        int sp = 0;
-        for (; sp + 8 <= splits; sp += 8) {           // eight independent loads in flight per thread (latency-bound otherwise)
+    // a CTA's elements are few (one input channel: HW*HW): several threads share an element, each summing a contiguous run of
+    // the K slices with all its loads in flight at once (one memory round trip instead of splits/8), partial sums combined in
+    // slice order through shared memory -- deterministic
+    const int n_elem = HW * c_n, n_pad = (n_elem + 31) & ~31;
+    const int parts = min((int)blockDim.x / n_pad, splits);
+    float *partial = slab + HW * cols;                // [parts][n_pad], behind the slab
+    if (parts >= 2) {
+        const int part = threadIdx.x / n_pad, e0 = threadIdx.x - part * n_pad;
+        if (part < parts && e0 < n_elem) {
+            const int e = (e0 / c_n) * cols + c_lo + e0 % c_n;
+            const int sp_lo = part * splits / parts, sp_hi = (part + 1) * splits / parts;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            int sp = sp_lo;
+            for (; sp + 4 <= sp_hi; sp += 4)
 #pragma unroll
-            for (int u = 0; u < 8; u++) acc[u] += __ldg(base + (long long)(sp + u) * split_stride + e);
+                for (int u = 0; u < 4; u++) acc[u] += __ldg(base + (long long)(sp + u) * split_stride + e);
+            for (; sp < sp_hi; sp++) acc[0] += __ldg(base + (long long)sp * split_stride + e);
+            partial[part * n_pad + e0] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
         }
-        for (; sp < splits; sp++) acc[0] += __ldg(base + (long long)sp * split_stride + e);
-        slab[e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+        __syncthreads();
+        if ((int)threadIdx.x < n_elem) {
+            const int e0 = threadIdx.x, e = (e0 / c_n) * cols + c_lo + e0 % c_n;
+            float sum = partial[e0];
+            for (int q = 1; q < parts; q++) sum += partial[q * n_pad + e0];
+            slab[e] = sum;
+        }
+    } else {
+        for (int e0 = threadIdx.x; e0 < n_elem; e0 += blockDim.x) {
+            const int e = (e0 / c_n) * cols + c_lo + e0 % c_n;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int sp = 0;
+            for (; sp + 8 <= splits; sp += 8) {           // eight independent loads in flight per thread (latency-bound otherwise)
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc[u] += __ldg(base + (long long)(sp + u) * split_stride + e);
+            }
+            for (; sp < splits; sp++) acc[0] += __ldg(base + (long long)sp * split_stride + e);
+            slab[e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+        }
     }
     __syncthreads();
     const int taps = kh * kw;
@@ -385,12 +413,16 @@ extern "C" int hrl_board_fold_many(const HrlFoldJob *jobs, int32_t n_jobs, void 
         HRL_REQUIRE(j.ddense && j.dw && j.splits >= 1 && j.Cout > 0 && j.Cin > 0 && j.kh > 0 && j.kw > 0 && j.H > 0 && j.W > 0 && (j.kh & 1) &&
                         (j.kw & 1),
                     HRL_ERR_BAD_ARG, "hrl_board_fold: NULL pointer or bad shape (odd kernels only)");
-        const size_t slab_bytes = (size_t)j.H * j.W * j.Cin * j.H * j.W * sizeof(float);
+        const size_t slab_bytes = (size_t)j.H * j.W * j.Cin * j.H * j.W * sizeof(float) + 512 * sizeof(float);      // + slice-run partials
         HRL_REQUIRE(slab_bytes <= 200 * 1024, HRL_ERR_UNSUPPORTED, "hrl_board_fold: Cin*(H*W)^2 = %zu floats exceed shared memory",
                     slab_bytes / sizeof(float));
         if (slab_bytes > slab_max) slab_max = slab_bytes;
         fj.job[k] = j;
-        int groups = (2 * kNumSM + j.Cout - 1) / j.Cout;       // (output channel, group of input channels) CTAs: about two per SM
+        // (output channel, group of input channels) CTAs: at least about two per SM, and few enough elements per CTA (<= 128) that
+        // several threads can share the K slices of one element
+        int groups = (2 * kNumSM + j.Cout - 1) / j.Cout;
+        const int cells2 = j.H * j.W * j.H * j.W, i_per = cells2 >= 128 ? 1 : 128 / cells2;
+        if (groups < (j.Cin + i_per - 1) / i_per) groups = (j.Cin + i_per - 1) / i_per;
         if (groups > j.Cin) groups = j.Cin;
         fj.groups[k] = groups;
         fj.first_block[k + 1] = fj.first_block[k] + j.Cout * groups;

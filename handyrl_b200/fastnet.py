@@ -224,6 +224,34 @@ def _is_conv_lstm_cell(m):
             and len(list(m.children())) == 1 and not isinstance(m, nn.Conv2d))
 
 
+def _is_torus_conv(m):
+    """Duck-typed wrap-around convolution as the reference writes it (hungry_geese.py:24-37): `edge_size` = half the kernel, an
+    unpadded `conv`, an optional `bn`; forward = concatenate the opposite edges on both axes, convolve, normalise."""
+    conv, edge = getattr(m, 'conv', None), getattr(m, 'edge_size', None)
+    return (isinstance(conv, nn.Conv2d) and isinstance(edge, tuple) and len(edge) == 2 and not isinstance(m, nn.Conv2d)
+            and tuple(conv.padding) == (0, 0) and conv.kernel_size == (2 * edge[0] + 1, 2 * edge[1] + 1) and conv.stride == (1, 1)
+            and conv.dilation == (1, 1) and conv.groups == 1 and hasattr(m, 'bn')
+            and all(name in ('conv', 'bn') for name, _ in m.named_children()))
+
+
+_TORUS_CLASSES = {}
+
+
+def _fused_torus_class(cls):
+    if cls not in _TORUS_CLASSES:
+        original = cls.forward
+
+        def forward(self, x):
+            from . import ops
+            if (x.dim() == 4 and x.is_cuda and x.shape[2] * x.shape[3] <= MAX_CELLS and getattr(self.conv, 'tensor_cores', True)
+                    and ops.conv_implicit_supported(x, self.conv.weight)):
+                h = ops.conv_implicit(x, self.conv.weight, self.conv.bias, True)      # the wrap lives in the neighbour table
+                return self.bn(h) if self.bn is not None else h
+            return original(self, x)
+        _TORUS_CLASSES[cls] = type('Fused' + cls.__name__, (cls,), {'forward': forward, '_hrl_original': cls})
+    return _TORUS_CLASSES[cls]
+
+
 def _fused_cell_class(cls):
     if cls not in _CELL_CLASSES:
         def forward(self, x, state):
@@ -252,6 +280,9 @@ def optimize_small_boards(model, tensor_cores=True):
             n += 1
         elif _is_conv_lstm_cell(m) and not hasattr(type(m), '_hrl_original'):
             m.__class__ = _fused_cell_class(type(m))
+            n += 1
+        elif _is_torus_conv(m) and not hasattr(type(m), '_hrl_original'):
+            m.__class__ = _fused_torus_class(type(m))
             n += 1
     return n
 

@@ -75,3 +75,44 @@ def test_rewritten_modules_use_the_implicit_products():
         y = net(x)
         assert ops.LAUNCHES['n'] > before
         assert (y.double() - ref(x.double())).abs().max().item() < 1e-4
+
+
+def test_reference_style_torus_convolution_is_recognised():
+    """The reference writes the wrap-around convolution as edge concatenation + an unpadded convolution (hungry_geese.py:24-37);
+    fastnet recognises the module by structure and runs it as the wrap-around implicit product, forward and backward."""
+    import torch.nn as nn
+    from handyrl_b200 import fastnet, ops
+
+    class TorusConv2d(nn.Module):          # restated from the reference's forward (not imported: no kaggle_environments here)
+        def __init__(self, input_dim, output_dim, kernel_size, bn):
+            super().__init__()
+            self.edge_size = (kernel_size[0] // 2, kernel_size[1] // 2)
+            self.conv = nn.Conv2d(input_dim, output_dim, kernel_size=kernel_size)
+            self.bn = nn.BatchNorm2d(output_dim) if bn else None
+
+        def forward(self, x):
+            h = torch.cat([x[:, :, :, -self.edge_size[1]:], x, x[:, :, :, :self.edge_size[1]]], dim=3)
+            h = torch.cat([h[:, :, -self.edge_size[0]:], h, h[:, :, :self.edge_size[0]]], dim=2)
+            h = self.conv(h)
+            return self.bn(h) if self.bn is not None else h
+
+    torch.manual_seed(3)
+    ref = TorusConv2d(32, 32, (3, 3), False).cuda().double()
+    net = TorusConv2d(32, 32, (3, 3), False).cuda()
+    net.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    assert fastnet.optimize_small_boards(net) >= 1
+    x = torch.randn(9, 32, 7, 11, device='cuda')
+    xs, xd = x.clone().requires_grad_(True), x.double().requires_grad_(True)
+    dy = torch.randn(9, 32, 7, 11, device='cuda')
+    before = ops.LAUNCHES['n']
+    fastnet.new_step()
+    y = net(xs)
+    y.backward(dy)
+    assert ops.LAUNCHES['n'] >= before + 3
+    yd = ref(xd)
+    yd.backward(dy.double())
+    assert (y.double() - yd).abs().max().item() < 1e-4
+    assert (xs.grad.double() - xd.grad).abs().max().item() < 1e-4
+    assert (net.conv.weight.grad.double() - ref.conv.weight.grad).abs().max().item() < 2e-3 * ref.conv.weight.grad.abs().max().item()
+    fastnet.restore(net)
+    assert type(net) is TorusConv2d
