@@ -515,26 +515,38 @@ def conv_implicit(x, w, b=None, wrap=False):
     return _ConvImplicit.apply(x, w, b, bool(wrap))
 
 
+def _is_channels_last(t):
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+
+
 class _LstmGates(torch.autograd.Function):
+    """The kernels index (sample, 4 gates x CS, ...) blocks.  A channels-last tensor is exactly that with sample := pixel and
+    CS := C (the gate maps of one pixel are contiguous), so channels-last gates (what the tensor-core convolution produces) are
+    processed in place, no layout copy, and h', c' come out channels-last for the next convolution."""
+
     @staticmethod
     def forward(ctx, gates, c_prev):
-        gates, c_prev = gates.contiguous(), c_prev.contiguous()
+        cl = _is_channels_last(gates)
+        fmt = torch.channels_last if cl else torch.contiguous_format
+        gates, c_prev = gates.contiguous(memory_format=fmt), c_prev.contiguous(memory_format=fmt)
         N, C4 = gates.shape[:2]
         S = gates[0, 0].numel()
-        h, c = torch.empty_like(c_prev), torch.empty_like(c_prev)
-        check(lib().hrl_lstm_gates_fwd(_ptr(gates), _ptr(c_prev), _ptr(h), _ptr(c), N, C4 // 4, S, _stream_ptr()))
+        h, c = torch.empty_like(c_prev), torch.empty_like(c_prev)          # (preserve_format: channels-last stays channels-last)
+        dims = (N * S, C4 // 4, 1) if cl else (N, C4 // 4, S)
+        check(lib().hrl_lstm_gates_fwd(_ptr(gates), _ptr(c_prev), _ptr(h), _ptr(c), *dims, _stream_ptr()))
         _count()
         ctx.save_for_backward(gates, c_prev)
+        ctx.dims, ctx.fmt = dims, fmt
         return h, c
 
     @staticmethod
     def backward(ctx, dh, dc):
         gates, c_prev = ctx.saved_tensors
-        N, C4 = gates.shape[:2]
-        S = gates[0, 0].numel()
         dgates, dc_prev = torch.empty_like(gates), torch.empty_like(c_prev)
-        check(lib().hrl_lstm_gates_bwd(_ptr(gates), _ptr(c_prev), _ptr(None if dh is None else dh.contiguous()),
-                                       _ptr(None if dc is None else dc.contiguous()), _ptr(dgates), _ptr(dc_prev), N, C4 // 4, S,
+        # (named, not temporaries: a converted copy freed before the launch is enqueued could be handed to the next conversion)
+        dh_ = None if dh is None else dh.contiguous(memory_format=ctx.fmt)
+        dc_ = None if dc is None else dc.contiguous(memory_format=ctx.fmt)
+        check(lib().hrl_lstm_gates_bwd(_ptr(gates), _ptr(c_prev), _ptr(dh_), _ptr(dc_), _ptr(dgates), _ptr(dc_prev), *ctx.dims,
                                        _stream_ptr()))
         _count()
         return dgates, dc_prev
@@ -551,26 +563,61 @@ def _mask_view(om):
     return om, om.stride(0)
 
 
+# The hidden-state kernels treat a leaf as (B, P, R) blocks and are elementwise inside a block, so any dense ordering of the
+# R elements works as long as every operand of a call shares it.  A leaf (B, P, C, H, W) whose (C, H, W) block is channels-last
+# (what a net built on the tensor-core convolutions hands back) is therefore used as it lies: no layout copies in the time loop.
+def _block_layout(t):
+    if t.is_contiguous():
+        return 'std'
+    if t.dim() == 5 and t.stride(0) == t.shape[1] * t.stride(1) and _is_channels_last(t.flatten(0, 1)):
+        return 'cl'
+    if _is_channels_last(t):
+        return 'cl'
+    return None
+
+
+def _as_block_layout(t, layout):
+    if layout == 'cl' and t.dim() in (4, 5):
+        if _block_layout(t) == 'cl':
+            return t
+        lead = t.shape[:-3]
+        return t.reshape(-1, *t.shape[-3:]).contiguous(memory_format=torch.channels_last).view(*lead, *t.shape[-3:])
+    return t.contiguous()
+
+
+def _empty_block_layout(shape, layout, device):
+    if layout == 'cl' and len(shape) in (4, 5):
+        lead = tuple(shape[:-3])
+        n = 1
+        for d in lead:
+            n *= d
+        return torch.empty((n,) + tuple(shape[-3:]), dtype=torch.float32, device=device,
+                           memory_format=torch.channels_last).view(*lead, *shape[-3:])
+    return torch.empty(tuple(shape), dtype=torch.float32, device=device)
+
+
 class _HiddenVisible(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, om, sum_players):
-        h = h.contiguous()
+        layout = _block_layout(h) or 'std'
+        h = _as_block_layout(h, layout)
         B, P = h.shape[:2]
         R = h[0, 0].numel()
         om, stride = _mask_view(om)
-        out = torch.empty((B,) + tuple(h.shape[2:]) if sum_players else h.shape, dtype=torch.float32, device=h.device)
+        out = _empty_block_layout((B,) + tuple(h.shape[2:]) if sum_players else tuple(h.shape), layout, h.device)
         check(lib().hrl_hidden_visible_fwd(_ptr(h), _ptr(om), stride, _ptr(out), B, P, R, int(sum_players), _stream_ptr()))
         _count()
         ctx.save_for_backward(om)
-        ctx.meta = (B, P, R, stride, bool(sum_players), tuple(h.shape))
+        ctx.meta = (B, P, R, stride, bool(sum_players), tuple(h.shape), layout)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         om, = ctx.saved_tensors
-        B, P, R, stride, sum_players, shape = ctx.meta
-        dh = torch.empty(shape, dtype=torch.float32, device=dout.device)
-        check(lib().hrl_hidden_visible_bwd(_ptr(dout.contiguous()), _ptr(om), stride, _ptr(dh), B, P, R, int(sum_players), _stream_ptr()))
+        B, P, R, stride, sum_players, shape, layout = ctx.meta
+        dh = _empty_block_layout(shape, layout, dout.device)
+        dout = _as_block_layout(dout, layout)
+        check(lib().hrl_hidden_visible_bwd(_ptr(dout), _ptr(om), stride, _ptr(dh), B, P, R, int(sum_players), _stream_ptr()))
         _count()
         return dh, None, None
 
@@ -578,25 +625,27 @@ class _HiddenVisible(torch.autograd.Function):
 class _HiddenBlend(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, nh, om):
-        h, nh = h.contiguous(), nh.contiguous()
+        layout = _block_layout(nh) or 'std'          # the net's output decides: it keeps coming back in that layout
+        h, nh = _as_block_layout(h, layout), _as_block_layout(nh, layout)
         B, P = h.shape[:2]
         Pn = nh.shape[1]
         R = h[0, 0].numel()
         om, stride = _mask_view(om)
-        out = torch.empty_like(h)
+        out = _empty_block_layout(tuple(h.shape), layout, h.device)
         check(lib().hrl_hidden_blend_fwd(_ptr(h), _ptr(nh), _ptr(om), stride, _ptr(out), B, P, Pn, R, _stream_ptr()))
         _count()
         ctx.save_for_backward(om)
-        ctx.meta = (B, P, Pn, R, stride, tuple(h.shape), tuple(nh.shape))
+        ctx.meta = (B, P, Pn, R, stride, tuple(h.shape), tuple(nh.shape), layout)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         om, = ctx.saved_tensors
-        B, P, Pn, R, stride, hshape, nshape = ctx.meta
-        dh = torch.empty(hshape, dtype=torch.float32, device=dout.device) if ctx.needs_input_grad[0] else None
-        dnh = torch.empty(nshape, dtype=torch.float32, device=dout.device)
-        check(lib().hrl_hidden_blend_bwd(_ptr(dout.contiguous()), _ptr(om), stride, _ptr(dh), _ptr(dnh), B, P, Pn, R, _stream_ptr()))
+        B, P, Pn, R, stride, hshape, nshape, layout = ctx.meta
+        dh = _empty_block_layout(hshape, layout, dout.device) if ctx.needs_input_grad[0] else None
+        dnh = _empty_block_layout(nshape, layout, dout.device)
+        dout = _as_block_layout(dout, layout)
+        check(lib().hrl_hidden_blend_bwd(_ptr(dout), _ptr(om), stride, _ptr(dh), _ptr(dnh), B, P, Pn, R, _stream_ptr()))
         _count()
         return dh, dnh, None
 

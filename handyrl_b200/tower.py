@@ -229,10 +229,13 @@ class FusedBoardNet:
         L = self.depth
         with torch.no_grad():
             g = lambda p_: p_.grad
+            # (named: a temporary copy freed before the launch could be handed to the next .contiguous())
+            dpolicy, dvalue = dpolicy.contiguous(), dvalue.contiguous()
+            dreturn = dreturn.contiguous() if self.rmaps else None
             check(lib().hrl_heads_bwd(_ptr(self.Hpre), self.ldh, M_, self.cells, self.pmaps, self.vmaps, self.rmaps, self.A, self.slope,
                                       _ptr(m.p_out.weight), _ptr(m.v_out.weight), _ptr(m.r_out.weight) if self.rmaps else None,
-                                      _ptr(self.value), _ptr(dpolicy.contiguous()), _ptr(dvalue.contiguous()),
-                                      _ptr(dreturn.contiguous()) if self.rmaps else None, _ptr(self.dHpre),
+                                      _ptr(self.value), _ptr(dpolicy), _ptr(dvalue),
+                                      _ptr(dreturn), _ptr(self.dHpre),
                                       _ptr(g(m.p_out.weight)), _ptr(g(m.v_out.weight)), _ptr(g(m.r_out.weight)) if self.rmaps else None,
                                       _ptr(g(m.p_squeeze.bias)), _ptr(g(m.v_squeeze.bias)), _ptr(g(m.r_squeeze.bias)) if self.rmaps else None,
                                       _ptr(self.heads_ws), _stream_ptr()))

@@ -151,3 +151,45 @@ def test_fused_conv_lstm_cell_rewrite_covers_reference_style_cells():
         torch.testing.assert_close(got[1], want[1], rtol=1e-5, atol=1e-6)
         fastnet.restore(holder)
         assert not type(cell).__name__.startswith('Fused')
+
+
+def test_gate_and_hidden_kernels_take_channels_last_blocks_as_they_lie():
+    """Channels-last gates (what the tensor-core convolution produces) and hidden leaves whose (C,H,W) blocks are channels-last go
+    through the same kernels without a layout copy: results equal the NCHW call, outputs keep the layout, gradients too."""
+    from handyrl_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(11)
+    N, C, H, W = 10, 8, 6, 6
+    gates = torch.randn(N, 4 * C, H, W, device='cuda', generator=g)
+    c0 = torch.randn(N, C, H, W, device='cuda', generator=g)
+    dh, dc = torch.randn(N, C, H, W, device='cuda', generator=g), torch.randn(N, C, H, W, device='cuda', generator=g)
+    res = {}
+    for cl in (False, True):
+        fmt = torch.channels_last if cl else torch.contiguous_format
+        gi = gates.clone(memory_format=fmt).requires_grad_(True)
+        ci = c0.clone(memory_format=fmt).requires_grad_(True)
+        h, c = ops.lstm_gates(gi, ci)
+        assert h.is_contiguous(memory_format=fmt) and c.is_contiguous(memory_format=fmt)
+        torch.autograd.backward([h, c], [dh, dc])
+        res[cl] = (h, c, gi.grad, ci.grad)
+    for a, b in zip(res[False], res[True]):
+        assert torch.equal(a.contiguous(), b.contiguous())
+
+    B, P = 5, 2
+    hstate = torch.randn(B, P, C, H, W, device='cuda', generator=g)
+    nh = torch.randn(B, P, C, H, W, device='cuda', generator=g)
+    om = (torch.rand(B, P, 1, device='cuda', generator=g) < 0.6).float()
+    dout = torch.randn(B, P, C, H, W, device='cuda', generator=g)
+    as_cl = lambda t: t.flatten(0, 1).contiguous(memory_format=torch.channels_last).unflatten(0, (B, P))
+    out = {}
+    for cl in (False, True):
+        hi = (as_cl(hstate) if cl else hstate.clone()).detach().requires_grad_(True)
+        ni = (as_cl(nh) if cl else nh.clone()).detach().requires_grad_(True)
+        vis = ops.hidden_visible(hi, om, False)
+        mix = ops.hidden_blend(hi, ni, om)
+        if cl:
+            assert ops._block_layout(vis) == 'cl' and ops._block_layout(mix) == 'cl'
+        (vis * dout).sum().backward(retain_graph=True)
+        (mix * dout.flip(0)).sum().backward()
+        out[cl] = (vis, mix, hi.grad, ni.grad)
+    for a, b in zip(out[False], out[True]):
+        assert torch.equal(a.contiguous(), b.contiguous())
