@@ -65,7 +65,8 @@ class HrlGemmArgs(C.Structure):
                 ('ep_y', C.c_void_p), ('ep_ldy', C.c_int64), ('ep_scale', C.c_void_p), ('ep_shift', C.c_void_p),
                 ('ep_mean', C.c_void_p), ('ep_rstd', C.c_void_p), ('col_partials', C.c_void_p),
                 ('conv_off', C.c_void_p), ('conv_mode', C.c_int32), ('conv_hw', C.c_int32), ('conv_taps', C.c_int32),
-                ('conv_cin', C.c_int32)]
+                ('conv_cin', C.c_int32), ('seg_a', C.c_void_p), ('seg_b', C.c_void_p), ('segments', C.c_int32),
+                ('conv_ones_row', C.c_int32)]
 
 
 MAX_BOARD_JOBS = 8
@@ -138,6 +139,7 @@ SYMBOLS = {
     'hrl_conv_geometry': (C.c_int, [C.c_int32] * 5 + [C.c_void_p]),
     'hrl_conv_pack_floats': (C.c_size_t, [C.c_int32] * 3),
     'hrl_conv_pack': (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 3),
+    'hrl_conv_wgrad_reduce2': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p]),
     'hrl_conv_wgrad_reduce': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'hrl_board_pack_many': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'hrl_board_fold_many': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),

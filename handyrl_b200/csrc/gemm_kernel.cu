@@ -42,6 +42,8 @@ constexpr int kMaxN = 288;          // columns of one CTA tile (TMEM: 512 fp32 c
 constexpr int kChunkK = 32;         // reduction elements per shared-memory stage
 constexpr int kStages = 3;
 
+constexpr int kMaxSegments = 64;     // (dy, x) pairs of one segmented weight-gradient product
+
 struct GemmOperand {
     const float *ptr, *ptr2;        // ptr2: optional second source with the same layout (operand = x*p + y*q + r), or NULL
     const float *p, *q, *r;         // per-feature constants of the operand transform, or NULL (plain operand)
@@ -73,6 +75,11 @@ struct GemmParams {
     //   mode 2 (weight gradient): the reduction runs over pixels, B row n is (tap, channel) = (n / cin, n % cin) of the shifted input.
     const short *conv_off;
     int conv_mode, conv_hw, conv_taps, conv_cin, conv_cpt;
+    // mode 2 over several (dy, x) pairs that share one weight (a recurrent cell applied at every time step): K slice `split`
+    // reads pair split / seg_splits -- ONE product per weight and backward pass instead of one per application
+    int seg_splits;                 // 0 = one pair (a.ptr / b.ptr)
+    int conv_ones;                  // 1: one more B row, all ones: its output column is sum_pixels dy = the bias gradient
+    const float *seg_a[kMaxSegments], *seg_b[kMaxSegments];
 };
 
 constexpr short kConvOutside = -32768;
@@ -208,6 +215,7 @@ __device__ __forceinline__ float4 load_item_conv(const Item &it, const float *ba
             int pos = pos0 + it.k() + e;
             if (hw >= kChunkK) pos -= pos >= hw ? hw : 0;
             else pos %= hw;
+            if (tap >= p.conv_taps) { r[e] = 1.f; continue; }          // the ones row (bias gradient)
             const short o = table[pos * p.conv_taps + tap];
             if (o != kConvOutside) r[e] = __ldg(base + (long long)(kk + o) * ld + ci);
         }
@@ -300,7 +308,9 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
     const int n_here = min(kMaxN, p.N - n0);
     const int rows_a = min(kTileM, p.M - m0);
     const int total_chunks = (p.K + kChunkK - 1) / kChunkK;
-    const int c_begin = split * p.chunks_per_split;
+    const int seg = p.seg_splits ? split / p.seg_splits : 0;
+    const int c_begin = (p.seg_splits ? split - seg * p.seg_splits : split) * p.chunks_per_split;
+    const float *a_base = p.seg_splits ? p.seg_a[seg] : p.a.ptr, *b_base = p.seg_splits ? p.seg_b[seg] : p.b.ptr;
     const int c_end = min(total_chunks, c_begin + p.chunks_per_split);
 
     // shared-memory stage: [B_hi | B_lo], each [rows][128 B] with the 16-byte slots of a row swizzled
@@ -342,7 +352,7 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
     const int a_row = a_q * 32 + lane;                   // row of the tile == TMEM lane
     const bool a_live = a_row < rows_a;
     const int a_k = 8 * a_g;                             // offset of the slice inside a chunk
-    const float *a_ptr = p.a.ptr + (A_K ? (long long)(m0 + a_row) * p.a.ld + a_k : (long long)a_k * p.a.ld + (m0 + a_row));
+    const float *a_ptr = a_base + (A_K ? (long long)(m0 + a_row) * p.a.ld + a_k : (long long)a_k * p.a.ld + (m0 + a_row));
     const long long a2 = p.a.ptr2 ? (p.a.ptr2 - p.a.ptr) : 0;
     const bool vec_a = A_K && (p.a.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a.ptr) & 15) == 0) &&
                        (!p.a.ptr2 || (reinterpret_cast<uintptr_t>(p.a.ptr2) & 15) == 0);
@@ -356,7 +366,7 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
 
     // ---- B: items as before
     const long long off_b = B_K ? (long long)n0 * p.b.ld : (long long)n0;
-    const float *Bg = p.b.ptr + off_b;
+    const float *Bg = b_base + off_b;
     const long long b2 = p.b.ptr2 ? (p.b.ptr2 - p.b.ptr) : 0;
     const bool vec_b = B_K && (p.b.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.b.ptr) & 15) == 0) &&
                        (!p.b.ptr2 || (reinterpret_cast<uintptr_t>(p.b.ptr2) & 15) == 0);
@@ -507,7 +517,7 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
                 // all the loads first (one exposed latency per chunk, not one per item), then the transforms
 #pragma unroll
                 for (int u = 0; u < ITEMS_B; u++)
-                    vb[u] = (!B_K && p.conv_mode == 2) ? load_item_conv(ib[u], p.b.ptr, p.b.ld, k0, k0 % p.conv_hw, p, conv_off_s)
+                    vb[u] = (!B_K && p.conv_mode == 2) ? load_item_conv(ib[u], b_base, p.b.ld, k0, k0 % p.conv_hw, p, conv_off_s)
                                                        : load_item<B_K>(ib[u], Bg, p.b.ld, vec_b, adv_b, k_left);
                 if (b_rows) {
 #pragma unroll
@@ -807,7 +817,7 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
     const HrlGemmArgs &g = *args;
     const int64_t M = g.M, N = g.N, K = g.K;
     int splits = g.splits;
-    HRL_REQUIRE(g.a.ptr && g.b.ptr && (g.C || (splits > 1 && g.workspace)), HRL_ERR_BAD_ARG, "hrl_gemm_fused: NULL pointer");
+    HRL_REQUIRE(g.a.ptr && g.b.ptr && (g.C || ((splits > 1 || g.segments > 0) && g.workspace)), HRL_ERR_BAD_ARG, "hrl_gemm_fused: NULL pointer");
     HRL_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 22) && K < (1ll << 31) && g.b.ld < (1ll << 22), HRL_ERR_BAD_ARG,
                 "hrl_gemm_fused: bad dimensions (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
     HRL_REQUIRE(g.conv_mode >= 0 && g.conv_mode <= 2, HRL_ERR_BAD_ARG, "hrl_gemm_fused: conv_mode is 0, 1 or 2");
@@ -822,10 +832,16 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
                         "hrl_gemm_fused: convolution forward needs a packed B image over taps x (channels padded to 32), 16-byte aligned "
                         "pixel rows and whole boards");
         else
-            HRL_REQUIRE(!g.b.packed && !g.a.kmajor && !g.b.kmajor && g.b.ld >= g.conv_cin && N == (int64_t)g.conv_taps * g.conv_cin &&
-                            K % g.conv_hw == 0,
-                        HRL_ERR_UNSUPPORTED, "hrl_gemm_fused: convolution weight gradient reduces over whole boards of pixels, N = taps x channels");
+            HRL_REQUIRE(!g.b.packed && !g.a.kmajor && !g.b.kmajor && g.b.ld >= g.conv_cin &&
+                            N == (int64_t)g.conv_taps * g.conv_cin + (g.conv_ones_row ? 1 : 0) && K % g.conv_hw == 0,
+                        HRL_ERR_UNSUPPORTED,
+                        "hrl_gemm_fused: convolution weight gradient reduces over whole boards of pixels, N = taps x channels (+ 1 with the ones row)");
     }
+    HRL_REQUIRE(g.segments >= 0 && g.segments <= hrl::kMaxSegments &&
+                    (g.segments == 0 || (g.conv_mode == 2 && g.seg_a && g.seg_b && g.workspace && g.C == nullptr)),
+                HRL_ERR_BAD_ARG, "hrl_gemm_fused: up to %d segments, of a convolution weight gradient left as slice partials in the workspace",
+                hrl::kMaxSegments);
+    HRL_REQUIRE(!g.conv_ones_row || g.conv_mode == 2, HRL_ERR_BAD_ARG, "hrl_gemm_fused: the ones row belongs to the convolution weight gradient");
     HRL_REQUIRE((g.conv_mode == 1 || g.a.ld >= (g.a.kmajor ? K : M)) && (g.b.packed || g.conv_mode == 2 || g.b.ld >= (g.b.kmajor ? K : N)) &&
                     (g.C == nullptr || g.ldc >= N),
                 HRL_ERR_BAD_ARG, "hrl_gemm_fused: leading dimension smaller than the row length");
@@ -842,7 +858,7 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
     const int total_chunks = (int)((K + kChunkK - 1) / kChunkK);
     if (splits < 1) splits = 1;
     if (splits > total_chunks) splits = total_chunks;
-    HRL_REQUIRE(splits == 1 || (g.workspace != nullptr && g.bias == nullptr && g.epilogue == HRL_GEMM_EP_STORE), HRL_ERR_WORKSPACE,
+    HRL_REQUIRE((splits == 1 && g.segments == 0) || (g.workspace != nullptr && g.bias == nullptr && g.epilogue == HRL_GEMM_EP_STORE), HRL_ERR_WORKSPACE,
                 "hrl_gemm_fused: a split-K product needs a workspace of hrl_gemm_workspace_floats() floats, no bias and the plain epilogue");
     const int n_tiles = (int)((N + kMaxN - 1) / kMaxN);
     const int n_widest = (int)(N < kMaxN ? N : kMaxN);
@@ -869,7 +885,14 @@ extern "C" int hrl_gemm_fused(const HrlGemmArgs *args, void *stream_) {
     p.conv_off = g.conv_off; p.conv_mode = g.conv_mode; p.conv_hw = g.conv_hw; p.conv_taps = g.conv_taps; p.conv_cin = g.conv_cin;
     p.conv_cpt = (g.conv_cin + kChunkK - 1) / kChunkK;
     splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;      // no empty slices
-    if (splits > 1) {
+    p.seg_splits = 0;
+    p.conv_ones = g.conv_ones_row ? 1 : 0;
+    if (g.segments > 0) {              // every (dy, x) pair gets `splits` K slices of its own
+        p.seg_splits = splits;
+        for (int i = 0; i < g.segments; i++) { p.seg_a[i] = g.seg_a[i]; p.seg_b[i] = g.seg_b[i]; }
+        splits *= g.segments;
+    }
+    if (splits > 1 || g.segments > 0) {
         p.C = g.workspace; p.ldc = N; p.c_split_stride = M * N;
     } else {
         p.C = g.C; p.ldc = g.ldc; p.c_split_stride = 0;

@@ -313,18 +313,30 @@ __global__ void conv_pack_kernel(const float *__restrict__ w, int Cout, int Cin,
     }
 }
 
-__global__ void conv_wgrad_reduce_kernel(const float *__restrict__ partials, int splits, float *__restrict__ dw, int Cout, int Cin, int taps) {
-    const long long n = (long long)Cout * Cin * taps;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-        const int t = (int)(idx % taps), ci = (int)((idx / taps) % Cin), co = (int)(idx / ((long long)taps * Cin));
-        const float *src = partials + (long long)co * taps * Cin + (long long)t * Cin + ci;
+__global__ void conv_wgrad_reduce_kernel(const float *__restrict__ partials, int splits, int ncols, float *__restrict__ dw,
+                                         float *__restrict__ db, int Cout, int Cin, int taps, int accumulate) {
+    const long long n = (long long)Cout * Cin * taps, slice = (long long)Cout * ncols;
+    const long long total = n + (db ? Cout : 0);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const float *src;
+        float *dst;
+        if (idx < n) {
+            const int t = (int)(idx % taps), ci = (int)((idx / taps) % Cin), co = (int)(idx / ((long long)taps * Cin));
+            src = partials + (long long)co * ncols + (long long)t * Cin + ci;
+            dst = dw + idx;
+        } else {                         // the ones row's column: the bias gradient
+            const int co = (int)(idx - n);
+            src = partials + (long long)co * ncols + (long long)taps * Cin;
+            dst = db + co;
+        }
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         int sp = 0;
         for (; sp + 4 <= splits; sp += 4)
 #pragma unroll
-            for (int u = 0; u < 4; u++) acc[u] += __ldg(src + (long long)(sp + u) * n);
-        for (; sp < splits; sp++) acc[0] += __ldg(src + (long long)sp * n);
-        dw[idx] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            for (int u = 0; u < 4; u++) acc[u] += __ldg(src + (long long)(sp + u) * slice);
+        for (; sp < splits; sp++) acc[0] += __ldg(src + (long long)sp * slice);
+        const float sum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        *dst = accumulate ? *dst + sum : sum;
     }
 }
 
@@ -359,12 +371,18 @@ extern "C" int hrl_conv_pack(const float *w, int32_t Cout, int32_t Cin, int32_t 
     return HRL_OK;
 }
 
-extern "C" int hrl_conv_wgrad_reduce(const float *partials, int32_t splits, float *dw, int32_t Cout, int32_t Cin, int32_t taps, void *stream) {
-    HRL_REQUIRE(partials && dw && splits >= 1 && Cout > 0 && Cin > 0 && taps > 0, HRL_ERR_BAD_ARG, "hrl_conv_wgrad_reduce: NULL pointer or bad shape");
-    conv_wgrad_reduce_kernel<<<grid_for((long long)Cout * Cin * taps), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partials, splits, dw, Cout,
-                                                                                                                         Cin, taps);
+extern "C" int hrl_conv_wgrad_reduce2(const float *partials, int32_t splits, int32_t ncols, float *dw, float *db, int32_t Cout, int32_t Cin,
+                                      int32_t taps, int32_t accumulate, void *stream) {
+    HRL_REQUIRE(partials && dw && splits >= 1 && Cout > 0 && Cin > 0 && taps > 0 && ncols >= taps * Cin + (db ? 1 : 0), HRL_ERR_BAD_ARG,
+                "hrl_conv_wgrad_reduce: NULL pointer or bad shape");
+    conv_wgrad_reduce_kernel<<<grid_for((long long)Cout * Cin * taps + Cout), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        partials, splits, ncols, dw, db, Cout, Cin, taps, accumulate);
     HRL_CUDA_CHECK(cudaGetLastError());
     return HRL_OK;
+}
+
+extern "C" int hrl_conv_wgrad_reduce(const float *partials, int32_t splits, float *dw, int32_t Cout, int32_t Cin, int32_t taps, void *stream) {
+    return hrl_conv_wgrad_reduce2(partials, splits, taps * Cin, dw, nullptr, Cout, Cin, taps, 0, stream);
 }
 
 extern "C" int hrl_board_pack_many(const HrlPackJob *jobs, int32_t n_jobs, void *stream) {

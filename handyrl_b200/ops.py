@@ -463,6 +463,61 @@ def _conv_product(pix, image, rows, cin, taps, table, hw, bias=None):
     return out
 
 
+# Deferred weight gradients.  A recurrent net applies the same convolution at every time step (and DRC cells several times per step):
+# computing its weight gradient per application means T x repeats small products, slice reductions and gradient accumulations --
+# ~1,000 launches of a 4,400-launch Geister step, in a chain that is launch-bound.  Inside `deferred_weight_gradients()` the backward of
+# conv_implicit only records its (dy, x) pair; on exit ONE segmented product per weight reduces over all its pairs (hrl_gemm_fused with
+# `segments`), its ones row yields the bias gradient, and hrl_conv_wgrad_reduce2 adds the result into weight.grad / bias.grad.
+_DEFER = {'on': False, 'pending': {}}
+
+
+class deferred_weight_gradients:
+    def __enter__(self):
+        assert not _DEFER['on']
+        _DEFER['on'], _DEFER['pending'] = True, {}
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        pending, _DEFER['pending'], _DEFER['on'] = _DEFER['pending'], {}, False
+        if exc_type is None:
+            for job in pending.values():
+                _flush_weight_gradient(job)
+        return False
+
+
+def _flush_weight_gradient(job):
+    w, b, pairs = job['w'], job['b'], job['pairs']
+    Cout, Cin, kh, kw = w.shape
+    taps, (table, hw) = kh * kw, job['geom']
+    ones = b is not None
+    ncols = taps * Cin + (1 if ones else 0)
+    pixels = pairs[0][0].shape[0]
+    tiles = ((Cout + 127) // 128) * ((ncols + 287) // 288)
+    for start in range(0, len(pairs), 64):
+        chunk = pairs[start:start + 64]
+        n = len(chunk)
+        per = lib().hrl_gemm_effective_splits(pixels, max(1, min(pixels // 64, 148 // (tiles * n))))
+        ws = torch.empty((n * per, Cout, ncols), dtype=torch.float32, device=w.device)
+        seg_a = (C.c_void_p * n)(*[dy2.data_ptr() for dy2, _ in chunk])
+        seg_b = (C.c_void_p * n)(*[x2.data_ptr() for _, x2 in chunk])
+        g = _capi.HrlGemmArgs()
+        g.a.ptr, g.a.ld, g.a.kmajor = _ptr(chunk[0][0]), Cout, 0
+        g.b.ptr, g.b.ld, g.b.kmajor = _ptr(chunk[0][1]), Cin, 0
+        g.C, g.ldc = None, ncols
+        g.M, g.N, g.K, g.splits, g.workspace = Cout, ncols, pixels, per, _ptr(ws)
+        g.conv_off, g.conv_mode, g.conv_hw, g.conv_taps, g.conv_cin = _ptr(table), 2, hw, taps, Cin
+        g.seg_a, g.seg_b = C.cast(seg_a, C.c_void_p), C.cast(seg_b, C.c_void_p)
+        g.segments, g.conv_ones_row = n, int(ones)
+        check(lib().hrl_gemm_fused(C.byref(g), _stream_ptr()))
+        for t, shape in ((w, w.shape), (b, None)):
+            if t is not None and t.grad is None:
+                t.grad = torch.zeros_like(t, memory_format=torch.contiguous_format)
+        assert w.grad.is_contiguous()
+        check(lib().hrl_conv_wgrad_reduce2(_ptr(ws), n * per, ncols, _ptr(w.grad), _ptr(b.grad) if ones else None, Cout, Cin, taps, 1,
+                                           _stream_ptr()))
+        _count(2)
+
+
 class _ConvImplicit(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, wrap):
@@ -474,6 +529,7 @@ class _ConvImplicit(torch.autograd.Function):
         y2 = _conv_product(x2, fwd, Cout, Cin, kh * kw, table, H * W, bias=b)
         ctx.save_for_backward(xl, w)
         ctx.wrap, ctx.has_bias = wrap, b is not None
+        ctx.params = (w, b)             # the Parameter objects themselves (their .grad is what a deferred flush accumulates into)
         return y2.view(N, H, W, Cout).permute(0, 3, 1, 2)           # logical NCHW, channels-last in memory
 
     @staticmethod
@@ -488,6 +544,13 @@ class _ConvImplicit(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             _, adj = _conv_images(w)
             dx = _conv_product(dy2, adj, Cin, Cout, taps, table, H * W).view(N, H, W, Cin).permute(0, 3, 1, 2)
+        pw, pb = ctx.params
+        if (ctx.needs_input_grad[1] and _DEFER['on'] and pw.is_leaf and (pb is None or (pb.is_leaf and ctx.needs_input_grad[2]))
+                and (pw.grad is None or pw.grad.is_contiguous())):
+            job = _DEFER['pending'].setdefault(pw.data_ptr(), {'w': pw, 'b': pb, 'pairs': [], 'geom': (table, H * W)})
+            if not job['pairs'] or job['pairs'][0][0].shape[0] == dy2.shape[0]:      # (pairs of one product cover the same pixels)
+                job['pairs'].append((dy2, xl.permute(0, 2, 3, 1).reshape(-1, Cin)))
+                return dx, None, None, None
         if ctx.needs_input_grad[1]:
             x2 = xl.permute(0, 2, 3, 1).reshape(-1, Cin)
             pixels, cols = x2.shape[0], taps * Cin

@@ -464,7 +464,8 @@ class LearnerStep:
             if 'return' in outs:
                 heads.append(outs['return'])
                 grads.append(buf.dreturn)
-            torch.autograd.backward(heads, grads)
+            with ops.deferred_weight_gradients():       # shared (recurrent) convolution weights: one product per weight, at the end
+                torch.autograd.backward(heads, grads)
         self.opt.extra_slots[:NUM_LOSS].copy_(buf.losses)     # the loss sums ride the gradient bucket
         if self.peer is not None:
             reduced = self.peer(self.opt.n_pad, self.opt.partials)      # all-reduce + norm partials, one kernel

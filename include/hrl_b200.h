@@ -261,6 +261,14 @@ typedef struct HrlGemmArgs {
      *                K = pixels, split over K slices; hrl_conv_wgrad_reduce sums the slices into the (Cout, Cin, kh, kw) gradient. */
     const int16_t *conv_off;
     int32_t conv_mode, conv_hw, conv_taps, conv_cin;
+    /* conv_mode 2 over several (dy, x) pairs that share ONE weight -- a recurrent cell applied at every time step: segments > 0,
+     * seg_a[i] / seg_b[i] (host arrays of device pointers, at most 64) replace a.ptr / b.ptr, every pair has K pixels and gets
+     * `splits` K slices; C must be NULL, the (segments * effective splits) slice partials stay in the workspace for
+     * hrl_conv_wgrad_reduce2.  conv_ones_row = 1 appends a B row of ones: N = taps * conv_cin + 1, and the last column of the result is
+     * sum_pixels dy = the bias gradient. */
+    const float *const *seg_a;
+    const float *const *seg_b;
+    int32_t segments, conv_ones_row;
 } HrlGemmArgs;
 
 #define HRL_CONV_OUTSIDE (-32768)
@@ -272,6 +280,10 @@ size_t hrl_conv_pack_floats(int32_t rows, int32_t channels, int32_t taps);
 int hrl_conv_pack(const float *w, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, float *image_fwd, float *image_adj, void *stream);
 /* dw[co][ci][a][b] = sum over slices of partials[s][co][(a*kw+b)*Cin + ci]  (fixed order) */
 int hrl_conv_wgrad_reduce(const float *partials, int32_t splits, float *dw, int32_t Cout, int32_t Cin, int32_t taps, void *stream);
+/* the same over partial rows of `ncols` floats (taps*Cin, or taps*Cin + 1 with the ones row: column taps*Cin -> db[co], may be NULL);
+ * accumulate != 0 adds to dw / db instead of overwriting them */
+int hrl_conv_wgrad_reduce2(const float *partials, int32_t splits, int32_t ncols, float *dw, float *db, int32_t Cout, int32_t Cin, int32_t taps,
+                           int32_t accumulate, void *stream);
 
 int hrl_gemm_fused(const HrlGemmArgs *args, void *stream);
 

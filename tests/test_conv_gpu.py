@@ -116,3 +116,54 @@ def test_reference_style_torus_convolution_is_recognised():
     assert (net.conv.weight.grad.double() - ref.conv.weight.grad).abs().max().item() < 2e-3 * ref.conv.weight.grad.abs().max().item()
     fastnet.restore(net)
     assert type(net) is TorusConv2d
+
+
+@pytest.mark.parametrize('wrap,bias,steps', [(False, True, 5), (True, False, 5), (False, True, 70)])
+def test_deferred_weight_gradients_of_a_shared_convolution(wrap, bias, steps):
+    """A recurrent cell applies ONE convolution several times per backward pass.  Inside ops.deferred_weight_gradients() the
+    applications only record their (dy, x) pairs; one segmented product per weight (+ its ones row for the bias) then adds the
+    summed gradient into weight.grad / bias.grad: same result as per-application products, and as float64 autograd."""
+    from handyrl_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(21)
+    N, Cin, Cout, H, W = 23, 16, 16, 6, 6
+    w = torch.nn.Parameter(torch.randn(Cout, Cin, 3, 3, device='cuda', generator=g) * 0.2)
+    b = torch.nn.Parameter(torch.randn(Cout, device='cuda', generator=g)) if bias else None
+    x0 = torch.randn(N, Cin, H, W, device='cuda', generator=g)
+
+    def run(conv, x):
+        if steps > 10:        # many applications side by side (a long chain of them is chaotic: nothing to compare)
+            return sum(torch.tanh(conv(x * (0.5 + i / steps))) for i in range(steps))
+        for _ in range(steps):                       # the output of one application feeds the next (as h does in a ConvLSTM)
+            x = torch.tanh(conv(x))
+        return x
+
+    dy = torch.randn(N, Cout, H, W, device='cuda', generator=g)
+    grads = {}
+    for mode in ('immediate', 'deferred'):
+        w.grad = torch.full_like(w, 0.5)                         # the flush must ADD to what is there (other uses of the weight)
+        if bias:
+            b.grad = None
+        ops.conv_weights_changed()
+        y = run(lambda t: ops.conv_implicit(t, w, b, wrap), x0)
+        before = ops.LAUNCHES['n']
+        if mode == 'deferred':
+            with ops.deferred_weight_gradients():
+                y.backward(dy)
+        else:
+            y.backward(dy)
+        grads[mode] = (w.grad.clone(), None if not bias else b.grad.clone(), ops.LAUNCHES['n'] - before)
+    assert grads['deferred'][2] < grads['immediate'][2]          # `steps` products + reductions became 1 + 1 (2 + 2 beyond 64 pairs)
+    wd = w.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+
+    def conv64(t):
+        if wrap:
+            return torch.nn.functional.conv2d(torch.nn.functional.pad(t, (1, 1, 1, 1), mode='circular'), wd, bd)
+        return torch.nn.functional.conv2d(t, wd, bd, padding=1)
+    run(conv64, x0.double()).backward(dy.double())
+    scale = wd.grad.abs().max().item()
+    for mode in grads:
+        assert (grads[mode][0].double() - 0.5 - wd.grad).abs().max().item() <= 3e-5 * scale, mode
+        if bias:
+            assert (grads[mode][1].double() - bd.grad).abs().max().item() <= 3e-5 * bd.grad.abs().max().item(), mode
+    assert (grads['deferred'][0] - grads['immediate'][0]).abs().max().item() <= 2e-5 * scale
