@@ -202,22 +202,22 @@ __device__ __forceinline__ float4 load_item(const Item &it, const float *base, l
 }
 
 // weight gradient of a convolution (conv_mode 2): the item's row is (tap, channel) = (off >> 16, off & 0xFFFF), its 4 reduction
-// elements are 4 consecutive pixels; each reads the pixel's tap neighbour (or nothing outside the board)
-__device__ __forceinline__ float4 load_item_conv(const Item &it, const float *base, long long ld, int k0, int pos0, const GemmParams &p,
-                                                 const short *table) {
+// elements are 4 consecutive pixels; each reads the pixel's tap neighbour (or nothing outside the board).  `src` is the chunk's
+// table [32 pixels][taps] of source pixels (-1 = outside / past the end), computed once per chunk by the producers together.
+__device__ __forceinline__ float4 load_item_conv(const Item &it, const float *base, long long ld, int k0, const GemmParams &p,
+                                                 const int *src) {
     float r[4] = {0.f, 0.f, 0.f, 0.f};
     if (it.live()) {
-        const int ci = it.off & 0xFFFF, tap = it.off >> 16, hw = p.conv_hw;
+        const int ci = it.off & 0xFFFF, tap = it.off >> 16;
+        if (tap >= p.conv_taps) {                    // the ones row (bias gradient)
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int kk = k0 + it.k() + e;
-            if (kk >= p.K) continue;
-            int pos = pos0 + it.k() + e;
-            if (hw >= kChunkK) pos -= pos >= hw ? hw : 0;
-            else pos %= hw;
-            if (tap >= p.conv_taps) { r[e] = 1.f; continue; }          // the ones row (bias gradient)
-            const short o = table[pos * p.conv_taps + tap];
-            if (o != kConvOutside) r[e] = __ldg(base + (long long)(kk + o) * ld + ci);
+            for (int e = 0; e < 4; e++) r[e] = (k0 + it.k() + e < p.K) ? 1.f : 0.f;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int sp = src[(it.k() + e) * p.conv_taps + tap];
+                if (sp >= 0) r[e] = __ldg(base + (long long)sp * ld + ci);
+            }
         }
     }
     return make_float4(r[0], r[1], r[2], r[3]);
@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
     __shared__ uint32_t tmem_base_slot;
     __shared__ float b_consts[2][kMaxN];     // per-row constants of a single-source B transform (no registers, no per-chunk loads)
     __shared__ short conv_off_s[kConvMaxTable];
+    __shared__ int conv_src_s[2][kChunkK * 9];      // conv_mode 2: source pixel of (pixel of the chunk, tap), two chunks in flight
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool issuer = warp == kGemmThreads / 32;
@@ -493,6 +494,16 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
             const int k_left = p.K - k0;
             const long long adv_b = B_K ? (long long)k0 : (long long)k0 * p.b.ld;
             float4 vb[ITEMS_B];
+            if (!PACKED && !B_K && p.conv_mode == 2) {
+                // source pixels of this chunk, once for all items: conv_src_s[it & 1][pixel][tap] (double-buffered: the readers of
+                // the previous chunk are past their loads before anybody reaches this chunk's barrier)
+                if (tid < kChunkK * p.conv_taps) {
+                    const int kkl = tid / p.conv_taps, tap = tid - kkl * p.conv_taps, kk = k0 + kkl;
+                    const short o = conv_off_s[(kk % p.conv_hw) * p.conv_taps + tap];
+                    conv_src_s[it & 1][tid] = (kk < p.K && o != kConvOutside) ? kk + o : -1;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kGemmThreads) : "memory");
+            }
             if (STAGED_A) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");               // my copies of this chunk have landed ...
                 asm volatile("bar.sync 1, %0;" ::"n"(kGemmThreads) : "memory");    // ... everybody's; and the other raw stage is free
@@ -517,7 +528,7 @@ __global__ void __launch_bounds__(kGemmBlock, 1) gemm_tf32x3_kernel(const GemmPa
                 // all the loads first (one exposed latency per chunk, not one per item), then the transforms
 #pragma unroll
                 for (int u = 0; u < ITEMS_B; u++)
-                    vb[u] = (!B_K && p.conv_mode == 2) ? load_item_conv(ib[u], b_base, p.b.ld, k0, k0 % p.conv_hw, p, conv_off_s)
+                    vb[u] = (!B_K && p.conv_mode == 2) ? load_item_conv(ib[u], b_base, p.b.ld, k0, p, conv_src_s[it & 1])
                                                        : load_item<B_K>(ib[u], Bg, p.b.ld, vec_b, adv_b, k_left);
                 if (b_rows) {
 #pragma unroll

@@ -489,8 +489,21 @@ def _flush_weight_gradient(job):
     w, b, pairs = job['w'], job['b'], job['pairs']
     Cout, Cin, kh, kw = w.shape
     taps, (table, hw) = kh * kw, job['geom']
-    ones = b is not None
-    ncols = taps * Cin + (1 if ones else 0)
+    # the ones row (bias gradient as one more column) is free unless that column opens a new 288-wide tile AND the extra tile's CTAs
+    # take K slices away from the others (a weight used once: 1 tile x 148 slices vs 2 tiles x 74): then a column sum does it
+    cols, pixels0 = taps * Cin, pairs[0][0].shape[0]
+    n0 = min(len(pairs), 64)
+
+    def slices(ncols_):
+        t_ = ((Cout + 127) // 128) * ((ncols_ + 287) // 288)
+        return lib().hrl_gemm_effective_splits(pixels0, max(1, min(pixels0 // 64, 148 // (t_ * n0))))
+    ones = b is not None and slices(cols + 1) >= slices(cols)
+    if b is not None and not ones:
+        if b.grad is None:
+            b.grad = torch.zeros_like(b)
+        for dy2, _ in pairs:
+            b.grad.add_(dy2.sum(0))
+    ncols = cols + (1 if ones else 0)
     pixels = pairs[0][0].shape[0]
     tiles = ((Cout + 127) // 128) * ((ncols + 287) // 288)
     for start in range(0, len(pairs), 64):
