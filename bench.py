@@ -16,7 +16,9 @@ metric = learner samples/s = B*T*steps/s over all GPUs (BASELINE.json).
                the part `e2e` starts after (Batcher.batch, reference train.py:317-318, 358)
   roofline     the fused loss kernel: algorithmic bytes / CUDA-event duration measured live in the timed region,
                against the measured HBM copy bandwidth (MEASURED_PEAKS.json); roofline_wide_rows: the same kernel alone
-               at the wide-row shape; roofline_k2: the replay gather/pad kernel alone
+               at the wide-row shape (roofline_wide_rows_bf16: with bf16 logit / gradient I/O); roofline_k2: the replay
+               gather/pad kernel alone; roofline_net_gemm (nets on the fused tower engine): the three tensor-core products
+               of one tower layer alone, bound = tensor, against the measured bf16 peak and the 3xTF32 ceiling peak/6
   cpu_baseline / --impl reference: the eager-PyTorch CPU port of the reference learner step (oracle/torch_learner.py,
                pinned to the reference's golden vectors) on the host cores: ALWAYS the workload's full batch, a fixed
                thread count, 3+ warm-ups, min / median / mean, loss-only and full step reported separately.
