@@ -417,13 +417,17 @@ def _conv_table(H, W, kh, kw, wrap, device):
 
 
 def _conv_images(w):
-    """The weight's packed forward / adjoint operand images, re-packed once per parameter generation."""
+    """The weight's packed forward / adjoint operand images, re-packed once per parameter generation.  (Keyed by address AND
+    identity: a freed model's weight address can be handed to another tensor of the same shape.)"""
+    import weakref
     Cout, Cin, kh, kw = w.shape
     key = (w.data_ptr(), tuple(w.shape))
     ent = _CONV_IMAGES.get(key)
-    if ent is None:
-        z = lambda rows, ch: torch.zeros(lib().hrl_conv_pack_floats(rows, ch, kh * kw), dtype=torch.float32, device=w.device)
-        ent = _CONV_IMAGES[key] = [z(Cout, Cin), z(Cin, Cout), None]
+    if ent is None or ent[3]() is not w:
+        if ent is None:
+            z = lambda rows, ch: torch.zeros(lib().hrl_conv_pack_floats(rows, ch, kh * kw), dtype=torch.float32, device=w.device)
+            ent = _CONV_IMAGES[key] = [z(Cout, Cin), z(Cin, Cout), None, None]
+        ent[2], ent[3] = None, weakref.ref(w)
     gen = (_CONV_GENERATION[0], w._version)
     if ent[2] != gen:
         check(lib().hrl_conv_pack(_ptr(w), Cout, Cin, kh, kw, _ptr(ent[0]), _ptr(ent[1]), _stream_ptr()))
@@ -554,10 +558,10 @@ class _ConvImplicit(torch.autograd.Function):
         table = _conv_table(H, W, kh, kw, ctx.wrap, xl.device)
         dyl, dy2 = _pixels(dy)
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            _, adj = _conv_images(w)
-            dx = _conv_product(dy2, adj, Cin, Cout, taps, table, H * W).view(N, H, W, Cin).permute(0, 3, 1, 2)
         pw, pb = ctx.params
+        if ctx.needs_input_grad[0]:
+            _, adj = _conv_images(pw)           # (the object forward saw: the image cache checks identity)
+            dx = _conv_product(dy2, adj, Cin, Cout, taps, table, H * W).view(N, H, W, Cin).permute(0, 3, 1, 2)
         if (ctx.needs_input_grad[1] and _DEFER['on'] and pw.is_leaf and (pb is None or (pb.is_leaf and ctx.needs_input_grad[2]))
                 and (pw.grad is None or pw.grad.is_contiguous())):
             job = _DEFER['pending'].setdefault(pw.data_ptr(), {'w': pw, 'b': pb, 'pairs': [], 'geom': (table, H * W)})
